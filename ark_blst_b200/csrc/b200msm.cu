@@ -1,0 +1,574 @@
+// Host side of the engine and the C-ABI of include/b200msm.h.
+// Replaces reference src/gpu.rs (SingleMultiexpKernel + msm, :45-241): planning (window width,
+// window count), device buffers, launches, and — unlike the reference, which downloads 18 944
+// partials and folds them on the host (:185-207) — the whole reduction stays on the device and
+// only the 144/288-byte result crosses PCIe.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200msm.h"
+#include "launch.h"
+
+using namespace b200msm;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(e__ == cudaErrorMemoryAllocation ? B200MSM_ENOMEM : B200MSM_ECUDA,   \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(B200MSM_ENOMEM, std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+        }
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Plan {
+    int c = 0, nwin = 0;
+    uint32_t nbw = 0, nb = 0;  // buckets per window, total
+    int key_bits = 0;
+};
+
+// SURVEY §8(d) work model, minimised over c; the same expression the roofline numerator uses.
+int auto_window(size_t n, bool g2) {
+    double madd = g2 ? 28 : 10, add = g2 ? 40 : 14, dbl = g2 ? 25 : 9;
+    double best = 1e300;
+    int bc = 2;
+    for (int c = 2; c <= 22; c++) {
+        double W = std::ceil(256.0 / c);
+        double cost = (double)n * W * (1.0 - std::pow(2.0, -c)) * madd + W * std::pow(2.0, c - 1) * 2 * add +
+                      W * (c * dbl + add);
+        if (cost < best) { best = cost; bc = c; }
+    }
+    return bc;
+}
+
+struct DeviceCtx {
+    int dev = -1;
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    DevBuf bases, scalars, keys[2], vals[2], cubtmp, start, cnt[2], ord[2], buckets, lvlR[2], lvlC[2], out;
+    cudaEvent_t ev[8] = {};
+    double phase_ms[8] = {};
+    int sm_count = 0;
+    void release_all() {
+        for (DevBuf *b : {&bases, &scalars, &keys[0], &keys[1], &vals[0], &vals[1], &cubtmp, &start, &cnt[0], &cnt[1],
+                          &ord[0], &ord[1], &buckets, &lvlR[0], &lvlR[1], &lvlC[0], &lvlC[1], &out})
+            b->release();
+    }
+};
+
+struct Engine {
+    std::mutex mu;
+    bool inited = false;
+    std::vector<std::unique_ptr<DeviceCtx>> ctx;
+    int window_override = 0;
+    bool profiling = false;
+};
+Engine g_eng;
+
+int engine_init_locked(int first, int ndev) {
+    if (g_eng.inited) return 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(B200MSM_ENODEV, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count=0"));
+    if (first < 0) {  // bind to whatever device is current (torch's, under torchrun)
+        if (cudaGetDevice(&first) != cudaSuccess) first = 0;
+        ndev = 1;
+    }
+    if (ndev <= 0) ndev = count - first;
+    if (first >= count || first + ndev > count) return fail(B200MSM_EINVAL, "device range out of bounds");
+    for (int d = first; d < first + ndev; d++) {
+        cudaDeviceProp p;
+        CUDA_TRY(cudaGetDeviceProperties(&p, d));
+        if (p.major != 10)
+            return fail(B200MSM_ENODEV, std::string("device ") + std::to_string(d) + " (" + p.name + ") is sm_" +
+                                            std::to_string(p.major * 10 + p.minor) + "; this build is sm_100a only");
+        auto c = std::make_unique<DeviceCtx>();
+        c->dev = d;
+        c->sm_count = p.multiProcessorCount;
+        CUDA_TRY(cudaSetDevice(d));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (auto &ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
+        g_eng.ctx.push_back(std::move(c));
+    }
+    g_eng.inited = true;
+    return 0;
+}
+int engine_init(int first, int ndev) {
+    std::lock_guard<std::mutex> lk(g_eng.mu);
+    return engine_init_locked(first, ndev);
+}
+DeviceCtx *ctx_for_current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    for (auto &c : g_eng.ctx)
+        if (c->dev == d) return c.get();
+    return nullptr;
+}
+
+// The pipeline on one device. Inputs already in device memory; d_out receives 3 field elements.
+// Must be called with ctx.mu held and ctx.dev current. Asynchronous on `st`.
+int run_group(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scalars_v, size_t n, int mont, void *d_out_v,
+              cudaStream_t st) {
+    if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "group must be B200MSM_G1 or B200MSM_G2");
+    const bool g2 = group == B200MSM_G2;
+    const uint32_t *d_bases = (const uint32_t *)d_bases_v, *d_scalars = (const uint32_t *)d_scalars_v;
+    uint32_t *d_out = (uint32_t *)d_out_v;
+    const int W = g2 ? 24 : 12;                      // u32 words per field element
+    const size_t PB = 4 * (size_t)W * sizeof(uint32_t);  // bytes per XYZZ point
+    if (n == 0) {
+        CUDA_TRY(cudaMemsetAsync(d_out, 0, 3 * W * 4, st));
+        return 0;
+    }
+    if (n >= (1ull << 31)) return fail(B200MSM_EINVAL, "n must be < 2^31 per device");
+    Plan pl;
+    pl.c = g_eng.window_override > 0 ? g_eng.window_override : auto_window(n, g2);
+    pl.c = std::max(2, std::min(pl.c, 24));
+    pl.nwin = (256 + pl.c - 1) / pl.c;  // c·W ≥ 256 > 255 = |r|: the top Booth carry stays inside
+    pl.nbw = 1u << (pl.c - 1);
+    pl.nb = pl.nbw * (uint32_t)pl.nwin;
+    pl.key_bits = 1;
+    while ((1ull << pl.key_bits) <= pl.nb) pl.key_bits++;  // keys run 0..nb inclusive (sentinel)
+    const size_t m = n * (size_t)pl.nwin;
+    const bool prof = g_eng.profiling;
+    int evi = 0;
+    auto mark = [&]() { if (prof) cudaEventRecord(cx.ev[evi++], st); };
+
+    for (int i = 0; i < 2; i++) {
+        if (int rc = cx.keys[i].reserve(m * 4)) return rc;
+        if (int rc = cx.vals[i].reserve(m * 4)) return rc;
+        if (int rc = cx.cnt[i].reserve((size_t)pl.nb * 4)) return rc;
+        if (int rc = cx.ord[i].reserve((size_t)pl.nb * 4)) return rc;
+        size_t lvl = (size_t)pl.nwin * std::max<size_t>(1, pl.nbw / 8) * PB;
+        if (int rc = cx.lvlR[i].reserve(lvl)) return rc;
+        if (int rc = cx.lvlC[i].reserve(lvl)) return rc;
+    }
+    if (int rc = cx.start.reserve(((size_t)pl.nb + 2) * 4)) return rc;
+    if (int rc = cx.buckets.reserve((size_t)pl.nb * PB)) return rc;
+    uint32_t *keys[2] = {cx.keys[0].as<uint32_t>(), cx.keys[1].as<uint32_t>()};
+    uint32_t *vals[2] = {cx.vals[0].as<uint32_t>(), cx.vals[1].as<uint32_t>()};
+    uint32_t *cnt[2] = {cx.cnt[0].as<uint32_t>(), cx.cnt[1].as<uint32_t>()};
+    uint32_t *ord[2] = {cx.ord[0].as<uint32_t>(), cx.ord[1].as<uint32_t>()};
+    uint32_t *start = cx.start.as<uint32_t>();
+    const int cnt_bits = 12;  // sizes above 4095 all sort first; finer order buys nothing
+    size_t tmp1 = 0, tmp2 = 0;
+    CUDA_TRY(sort_pairs(nullptr, &tmp1, keys[0], keys[1], vals[0], vals[1], m, pl.key_bits, false, nullptr, st));
+    CUDA_TRY(sort_pairs(nullptr, &tmp2, cnt[0], cnt[1], ord[0], ord[1], pl.nb, cnt_bits, true, nullptr, st));
+    if (int rc = cx.cubtmp.reserve(std::max(tmp1, tmp2))) return rc;
+
+    mark();
+    // 1. signed window digits → (bucket key, point index|sign)
+    launch_digits(d_scalars, n, mont, pl.c, pl.nwin, keys[0], vals[0], st);
+    mark();
+    // 2. radix sort by bucket key
+    int sel = 0;
+    CUDA_TRY(sort_pairs(cx.cubtmp.p, &tmp1, keys[0], keys[1], vals[0], vals[1], m, pl.key_bits, false, &sel, st));
+    mark();
+    // 3. bucket offsets, then buckets in decreasing-size order
+    launch_bounds(keys[sel], m, pl.nb, start, st);
+    launch_counts(start, pl.nb, (1u << cnt_bits) - 1, cnt[0], ord[0], st);
+    int osel = 0;
+    CUDA_TRY(sort_pairs(cx.cubtmp.p, &tmp2, cnt[0], cnt[1], ord[0], ord[1], pl.nb, cnt_bits, true, &osel, st));
+    mark();
+    // 4. bucket accumulation
+    (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals[sel], start, ord[osel], pl.nb, cx.buckets.as<uint32_t>(), st);
+    mark();
+    // 5. per-window weighted bucket sums, by levels
+    const uint32_t *X = cx.buckets.as<uint32_t>();
+    const uint32_t *Cin = nullptr;
+    uint32_t len = pl.nbw;
+    int log2M = 0, pp = 0;
+    while (len > 1) {
+        uint32_t seg = len >= 4096 ? 32 : (len >= 64 ? 8 : len);
+        (g2 ? launch_wsum_level_g2 : launch_wsum_level_g1)(X, Cin, len, seg, log2M, (uint32_t)pl.nwin,
+                                                           cx.lvlR[pp].as<uint32_t>(), cx.lvlC[pp].as<uint32_t>(), st);
+        X = cx.lvlR[pp].as<uint32_t>();
+        Cin = cx.lvlC[pp].as<uint32_t>();
+        int l2 = 0;
+        while ((1u << l2) < seg) l2++;
+        log2M += l2;
+        len /= seg;
+        pp ^= 1;
+    }
+    mark();
+    // 6. windows → one Jacobian point
+    (g2 ? launch_combine_g2 : launch_combine_g1)(Cin, X, pl.nwin, pl.c, d_out, st);
+    mark();
+    CUDA_TRY(cudaGetLastError());
+    if (prof) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        float ms;
+        for (int i = 0; i < 6; i++) {
+            cudaEventElapsedTime(&ms, cx.ev[i], cx.ev[i + 1]);
+            cx.phase_ms[i] = ms;
+        }
+        cudaEventElapsedTime(&ms, cx.ev[0], cx.ev[6]);
+        cx.phase_ms[6] = ms;
+        cx.phase_ms[7] = 1;
+    }
+    return 0;
+}
+
+size_t aff_bytes(int group) { return group == B200MSM_G2 ? 192 : 96; }
+size_t jac_bytes(int group) { return group == B200MSM_G2 ? 288 : 144; }
+
+// host-buffer MSM over the bound devices: shard by index range, one partial per device, final
+// addition on the first device.
+int msm_host(int group, const uint64_t *bases, const uint64_t *scalars, size_t n, int mont, uint64_t *out,
+             const struct b200msm_bases *resident);
+
+}  // namespace
+
+struct b200msm_bases {
+    int group;
+    size_t n;
+    std::vector<DevBuf> shard;      // one per bound device
+    std::vector<size_t> lo, cnt;    // index range per device
+};
+
+namespace {
+
+int msm_host(int group, const uint64_t *bases, const uint64_t *scalars, size_t n, int mont, uint64_t *out,
+             const b200msm_bases *resident) {
+    if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "bad group");
+    if (!out || (n && (!scalars || (!bases && !resident)))) return fail(B200MSM_EINVAL, "null pointer");
+    if (int rc = engine_init(-1, 1)) return rc;
+    const size_t AB = aff_bytes(group), JB = jac_bytes(group);
+    const int ndev = (int)g_eng.ctx.size();
+    if (n == 0) {
+        memset(out, 0, JB);
+        return 0;
+    }
+    int prev_dev = 0;
+    cudaGetDevice(&prev_dev);
+    // index ranges: the upload's own split when resident, else an even split
+    std::vector<size_t> lo(ndev), cnt(ndev);
+    for (int d = 0; d < ndev; d++) {
+        if (resident) {
+            lo[d] = resident->lo[d];
+            cnt[d] = lo[d] >= n ? 0 : std::min(resident->cnt[d], n - lo[d]);
+        } else {
+            lo[d] = n * d / ndev;
+            cnt[d] = n * (d + 1) / ndev - lo[d];
+        }
+    }
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (auto &c : g_eng.ctx) locks.emplace_back(c->mu);
+    int rc = 0;
+    // issue everything asynchronously on every device, then collect
+    for (int d = 0; d < ndev && !rc; d++) {
+        DeviceCtx &cx = *g_eng.ctx[d];
+        cudaSetDevice(cx.dev);
+        if ((rc = cx.out.reserve(JB * (size_t)(ndev + 1)))) break;
+        if (cnt[d] == 0) {
+            cudaMemsetAsync(cx.out.p, 0, JB, cx.stream);
+            continue;
+        }
+        if ((rc = cx.scalars.reserve(cnt[d] * 32))) break;
+        cudaMemcpyAsync(cx.scalars.p, scalars + 4 * lo[d], cnt[d] * 32, cudaMemcpyHostToDevice, cx.stream);
+        const void *db;
+        if (resident) db = resident->shard[d].p;
+        else {
+            if ((rc = cx.bases.reserve(cnt[d] * AB))) break;
+            cudaMemcpyAsync(cx.bases.p, (const char *)bases + lo[d] * AB, cnt[d] * AB, cudaMemcpyHostToDevice, cx.stream);
+            db = cx.bases.p;
+        }
+        rc = run_group(group, cx, db, cx.scalars.p, cnt[d], mont, cx.out.p, cx.stream);
+    }
+    if (!rc) {
+        DeviceCtx &c0 = *g_eng.ctx[0];
+        if (ndev == 1) {
+            cudaSetDevice(c0.dev);
+            cudaMemcpyAsync(out, c0.out.p, JB, cudaMemcpyDeviceToHost, c0.stream);
+            cudaError_t e = cudaStreamSynchronize(c0.stream);
+            if (e != cudaSuccess) rc = fail(B200MSM_ECUDA, std::string("msm: ") + cudaGetErrorString(e));
+        } else {
+            // gather the per-device partials on device 0 (peer copies over NVLink), add, download
+            for (int d = 1; d < ndev && !rc; d++) {
+                DeviceCtx &cx = *g_eng.ctx[d];
+                cudaSetDevice(cx.dev);
+                cudaError_t e = cudaStreamSynchronize(cx.stream);
+                if (e != cudaSuccess) { rc = fail(B200MSM_ECUDA, std::string("msm shard: ") + cudaGetErrorString(e)); break; }
+                cudaMemcpyPeerAsync((char *)c0.out.p + JB * (size_t)d, c0.dev, cx.out.p, cx.dev, JB, c0.stream);
+            }
+            if (!rc) {
+                cudaSetDevice(c0.dev);
+                void *sum = (char *)c0.out.p + JB * (size_t)ndev;
+                (group == B200MSM_G1 ? launch_sum_partials_g1 : launch_sum_partials_g2)((const uint32_t *)c0.out.p, ndev, (uint32_t *)sum, c0.stream);
+                cudaMemcpyAsync(out, sum, JB, cudaMemcpyDeviceToHost, c0.stream);
+                cudaError_t e = cudaStreamSynchronize(c0.stream);
+                if (e != cudaSuccess) rc = fail(B200MSM_ECUDA, std::string("msm combine: ") + cudaGetErrorString(e));
+            }
+        }
+    }
+    cudaSetDevice(prev_dev);
+    return rc;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int b200msm_init(int first_device, int n_devices) { return engine_init(first_device, n_devices); }
+
+void b200msm_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_eng.mu);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (auto &c : g_eng.ctx) {
+        std::lock_guard<std::mutex> l2(c->mu);
+        cudaSetDevice(c->dev);
+        cudaStreamSynchronize(c->stream);
+        c->release_all();
+        for (auto &ev : c->ev) cudaEventDestroy(ev);
+        cudaStreamDestroy(c->stream);
+    }
+    g_eng.ctx.clear();
+    g_eng.inited = false;
+    cudaSetDevice(prev);
+}
+int b200msm_device_count(void) { return (int)g_eng.ctx.size(); }
+const char *b200msm_last_error(void) { return g_err.c_str(); }
+const char *b200msm_version(void) { return "b200msm 0.1 (sm_100a)"; }
+
+int b200msm_g1(const uint64_t *bases, const uint64_t *scalars, size_t n, int mont, uint64_t out[18]) {
+    return msm_host(B200MSM_G1, bases, scalars, n, mont, out, nullptr);
+}
+int b200msm_g2(const uint64_t *bases, const uint64_t *scalars, size_t n, int mont, uint64_t out[36]) {
+    return msm_host(B200MSM_G2, bases, scalars, n, mont, out, nullptr);
+}
+
+int b200msm_bases_upload(int group, const uint64_t *bases, size_t n, b200msm_bases **handle) {
+    if (!handle || (n && !bases)) return fail(B200MSM_EINVAL, "null pointer");
+    if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "bad group");
+    if (int rc = engine_init(-1, 1)) return rc;
+    auto h = std::make_unique<b200msm_bases>();
+    h->group = group;
+    h->n = n;
+    const int ndev = (int)g_eng.ctx.size();
+    const size_t AB = aff_bytes(group);
+    h->shard.resize(ndev);
+    h->lo.resize(ndev);
+    h->cnt.resize(ndev);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    int rc = 0;
+    for (int d = 0; d < ndev && !rc; d++) {
+        h->lo[d] = n * d / ndev;
+        h->cnt[d] = n * (d + 1) / ndev - h->lo[d];
+        cudaSetDevice(g_eng.ctx[d]->dev);
+        if (h->cnt[d] == 0) continue;
+        if ((rc = h->shard[d].reserve(h->cnt[d] * AB))) break;
+        cudaError_t e = cudaMemcpy(h->shard[d].p, (const char *)bases + h->lo[d] * AB, h->cnt[d] * AB, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = fail(B200MSM_ECUDA, std::string("upload: ") + cudaGetErrorString(e));
+    }
+    cudaSetDevice(prev);
+    if (rc) {
+        for (auto &s : h->shard) s.release();
+        return rc;
+    }
+    *handle = h.release();
+    return 0;
+}
+int b200msm_bases_free(b200msm_bases *h) {
+    if (!h) return 0;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (size_t d = 0; d < h->shard.size() && d < g_eng.ctx.size(); d++) {
+        cudaSetDevice(g_eng.ctx[d]->dev);
+        h->shard[d].release();
+    }
+    cudaSetDevice(prev);
+    delete h;
+    return 0;
+}
+int b200msm_run(const b200msm_bases *h, const uint64_t *scalars, size_t n, int mont, uint64_t *out) {
+    if (!h) return fail(B200MSM_EINVAL, "null handle");
+    if (n > h->n) return fail(B200MSM_EINVAL, "n exceeds the uploaded base count");
+    return msm_host(h->group, nullptr, scalars, n, mont, out, h);
+}
+
+int b200msm_run_device(int group, const void *d_bases, const void *d_scalars, size_t n, int mont, void *d_out,
+                       void *stream) {
+    if (!d_out || (n && (!d_bases || !d_scalars))) return fail(B200MSM_EINVAL, "null pointer");
+    if (int rc = engine_init(-1, 1)) return rc;
+    DeviceCtx *cx = ctx_for_current_device();
+    if (!cx) return fail(B200MSM_EINVAL, "current device is not bound to the engine");
+    std::lock_guard<std::mutex> lk(cx->mu);
+    return run_group(group, *cx, d_bases, d_scalars, n, mont, d_out, (cudaStream_t)stream);
+}
+int b200msm_sum_partials_device(int group, const void *d_partials, int count, void *d_out, void *stream) {
+    if (!d_partials || !d_out || count < 0) return fail(B200MSM_EINVAL, "bad argument");
+    if (group == B200MSM_G1) launch_sum_partials_g1((const uint32_t *)d_partials, count, (uint32_t *)d_out, (cudaStream_t)stream);
+    else if (group == B200MSM_G2) launch_sum_partials_g2((const uint32_t *)d_partials, count, (uint32_t *)d_out, (cudaStream_t)stream);
+    else return fail(B200MSM_EINVAL, "bad group");
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int b200msm_set_window_bits(int c) {
+    if (c < 0 || c == 1 || c > 24) return fail(B200MSM_EINVAL, "window bits must be 0 (auto) or 2..24");
+    g_eng.window_override = c;
+    return 0;
+}
+int b200msm_set_profiling(int on) {
+    g_eng.profiling = on != 0;
+    return 0;
+}
+int b200msm_last_phase_ms(double out[8]) {
+    if (!g_eng.inited) return fail(B200MSM_EINVAL, "engine not initialised");
+    DeviceCtx *cx = ctx_for_current_device();
+    if (!cx) cx = g_eng.ctx[0].get();
+    memcpy(out, cx->phase_ms, sizeof cx->phase_ms);
+    return 0;
+}
+
+int b200msm_synth_bases_device(int group, uint64_t seed, size_t n, void *d_out, void *stream) {
+    if (!d_out && n) return fail(B200MSM_EINVAL, "null pointer");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (group == B200MSM_G1) launch_synth_bases_g1(seed, n, (uint32_t *)d_out, st);
+    else if (group == B200MSM_G2) launch_synth_bases_g2(seed, n, (uint32_t *)d_out, st);
+    else return fail(B200MSM_EINVAL, "bad group");
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int b200msm_synth_scalars_device(uint64_t seed, size_t n, int montgomery, void *d_out, void *stream) {
+    if (!d_out && n) return fail(B200MSM_EINVAL, "null pointer");
+    if (n == 0) return 0;
+    launch_synth_scalars(seed, n, montgomery, (uint32_t *)d_out, (cudaStream_t)stream);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int b200msm_imad_peak(double out[3]) {
+    cudaDeviceProp p;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaGetDeviceProperties(&p, dev));
+    const int blocks = p.multiProcessorCount * 4, threads = 256, iters = 2000;
+    uint32_t *buf = nullptr;
+    CUDA_TRY(cudaMalloc(&buf, (size_t)blocks * threads * 4));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double rate[2] = {0, 0};
+    for (int mode = 0; mode < 2; mode++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            cudaEventRecord(e0);
+            launch_imad_peak(mode, blocks, threads, buf, rep ? iters : 10, 0);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep && ms < best) best = ms;
+        }
+        double ops = (double)blocks * threads * iters * 64.0 * 8.0 * (mode == 1 ? 2.0 : 1.0);
+        rate[mode] = ops / (best * 1e-3);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    CUDA_TRY(cudaGetLastError());
+    out[0] = rate[0];
+    out[1] = rate[1];
+    out[2] = rate[0] / (64.0 * p.multiProcessorCount) / 1e6;  // MHz if the pipe issues 64 IMAD/clk/SM
+    return 0;
+}
+
+// ---- unit hooks ----
+int b200msm_dbg_field_op(int is_fp2, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
+    if (n == 0) return 0;
+    const size_t EB = is_fp2 ? 96 : 48;
+    uint32_t *da = nullptr, *db = nullptr, *dout = nullptr;
+    CUDA_TRY(cudaMalloc(&da, n * EB));
+    CUDA_TRY(cudaMalloc(&db, n * EB));
+    CUDA_TRY(cudaMalloc(&dout, n * EB));
+    CUDA_TRY(cudaMemcpy(da, a, n * EB, cudaMemcpyHostToDevice));
+    if (b) CUDA_TRY(cudaMemcpy(db, b, n * EB, cudaMemcpyHostToDevice));
+    launch_dbg_field_op(is_fp2, op, da, db, dout, n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, dout, n * EB, cudaMemcpyDeviceToHost));
+    cudaFree(da);
+    cudaFree(db);
+    cudaFree(dout);
+    return 0;
+}
+int b200msm_dbg_point_op(int group, int op, const uint64_t *acc, const uint64_t *q, uint64_t *out, size_t n) {
+    if (n == 0) return 0;
+    const size_t FB = group == B200MSM_G2 ? 96 : 48;
+    const size_t QB = (op == 0 ? 2 : 4) * FB;
+    uint32_t *dacc = nullptr, *dq = nullptr, *dout = nullptr;
+    CUDA_TRY(cudaMalloc(&dacc, n * 4 * FB));
+    CUDA_TRY(cudaMalloc(&dq, n * QB));
+    CUDA_TRY(cudaMalloc(&dout, n * 3 * FB));
+    CUDA_TRY(cudaMemcpy(dacc, acc, n * 4 * FB, cudaMemcpyHostToDevice));
+    if (q && op != 2) CUDA_TRY(cudaMemcpy(dq, q, n * QB, cudaMemcpyHostToDevice));
+    (group == B200MSM_G2 ? launch_dbg_point_op_g2 : launch_dbg_point_op_g1)(op, dacc, dq, dout, n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, dout, n * 3 * FB, cudaMemcpyDeviceToHost));
+    cudaFree(dacc);
+    cudaFree(dq);
+    cudaFree(dout);
+    return 0;
+}
+int b200msm_dbg_digits(const uint64_t *scalars, size_t n, int montgomery, int c, int32_t *out, int *nwin) {
+    if (c < 2 || c > 24 || !out || !nwin) return fail(B200MSM_EINVAL, "bad argument");
+    int W = (256 + c - 1) / c;
+    *nwin = W;
+    if (n == 0) return 0;
+    uint32_t *ds = nullptr;
+    int *dout = nullptr;
+    CUDA_TRY(cudaMalloc(&ds, n * 32));
+    CUDA_TRY(cudaMalloc(&dout, n * (size_t)W * 4));
+    CUDA_TRY(cudaMemcpy(ds, scalars, n * 32, cudaMemcpyHostToDevice));
+    launch_digits_dbg(ds, n, montgomery, c, W, dout, 0);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, dout, n * (size_t)W * 4, cudaMemcpyDeviceToHost));
+    cudaFree(ds);
+    cudaFree(dout);
+    return 0;
+}
+
+}  // extern "C"

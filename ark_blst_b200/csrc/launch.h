@@ -1,0 +1,49 @@
+// Host-callable launchers, one translation unit per kernel family × group so the heavy field code
+// compiles in parallel (and only once per change).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace b200msm {
+
+// k_prep.cu
+void launch_digits(const uint32_t *scalars, size_t n, int mont, int c, int nwin, uint32_t *keys, uint32_t *vals,
+                   cudaStream_t st);
+void launch_digits_dbg(const uint32_t *scalars, size_t n, int mont, int c, int nwin, int *out, cudaStream_t st);
+void launch_bounds(const uint32_t *keys, size_t m, uint32_t nb, uint32_t *start, cudaStream_t st);
+void launch_counts(const uint32_t *start, uint32_t nb, uint32_t clampv, uint32_t *cnt, uint32_t *ids, cudaStream_t st);
+// radix sort of (key,val) u32 pairs on bits [0,end_bit). Double buffers: result lands in
+// k[*sel]/v[*sel]. tmp == nullptr → size query only.
+cudaError_t sort_pairs(void *tmp, size_t *tmp_bytes, uint32_t *k0, uint32_t *k1, uint32_t *v0, uint32_t *v1, size_t m,
+                       int end_bit, bool descending, int *sel, cudaStream_t st);
+
+// k_accumulate_g{1,2}.cu
+void launch_accumulate_g1(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
+                          uint32_t nb, uint32_t *buckets, cudaStream_t st);
+void launch_accumulate_g2(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
+                          uint32_t nb, uint32_t *buckets, cudaStream_t st);
+
+// k_reduce_g{1,2}.cu
+void launch_wsum_level_g1(const uint32_t *X, const uint32_t *Cin, uint32_t len, uint32_t m, int log2M, uint32_t nwin,
+                          uint32_t *Rout, uint32_t *Cout, cudaStream_t st);
+void launch_wsum_level_g2(const uint32_t *X, const uint32_t *Cin, uint32_t len, uint32_t m, int log2M, uint32_t nwin,
+                          uint32_t *Rout, uint32_t *Cout, cudaStream_t st);
+void launch_combine_g1(const uint32_t *C, const uint32_t *R, int nwin, int c, uint32_t *out, cudaStream_t st);
+void launch_combine_g2(const uint32_t *C, const uint32_t *R, int nwin, int c, uint32_t *out, cudaStream_t st);
+void launch_sum_partials_g1(const uint32_t *partials, int count, uint32_t *out, cudaStream_t st);
+void launch_sum_partials_g2(const uint32_t *partials, int count, uint32_t *out, cudaStream_t st);
+
+// k_synth_g{1,2}.cu / k_util.cu
+void launch_synth_bases_g1(uint64_t seed, size_t n, uint32_t *out, cudaStream_t st);
+void launch_synth_bases_g2(uint64_t seed, size_t n, uint32_t *out, cudaStream_t st);
+void launch_synth_scalars(uint64_t seed, size_t n, int mont, uint32_t *out, cudaStream_t st);
+void launch_imad_peak(int mode, int blocks, int threads, uint32_t *buf, int iters, cudaStream_t st);
+void launch_dbg_field_op(int is_fp2, int op, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n);
+void launch_dbg_point_op_g1(int op, const uint32_t *acc, const uint32_t *q, uint32_t *out, size_t n);
+void launch_dbg_point_op_g2(int op, const uint32_t *acc, const uint32_t *q, uint32_t *out, size_t n);
+
+inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace b200msm

@@ -1,0 +1,73 @@
+// Scalar-side device helpers: Fr canonicalisation and Booth window digits.
+#pragma once
+#include <cstdint>
+
+namespace b200msm {
+
+// ---- Fr: canonicalise the scalar (reference src/scalar.rs:450-463 does this on the host with a
+// BigUint allocation per element; here it is 8 limbs of Montgomery reduction on the device) ----
+__device__ __constant__ const uint32_t FR_MOD[8] = {0x00000001, 0xffffffff, 0xfffe5bfe, 0x53bda402,
+                                                    0x09a1d805, 0x3339d808, 0x299d7d48, 0x73eda753};
+
+__device__ __forceinline__ bool fr_geq_r(const uint32_t *s) {
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+        if (s[i] > FR_MOD[i]) return true;
+        if (s[i] < FR_MOD[i]) return false;
+    }
+    return true;
+}
+__device__ __forceinline__ void fr_sub_r(uint32_t *s) {
+    uint64_t brw = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)s[i] - FR_MOD[i] - brw;
+        s[i] = (uint32_t)d;
+        brw = (d >> 32) & 1;
+    }
+}
+// s ← s·2^-256 mod r  (Montgomery form → canonical integer); -r^-1 mod 2^32 = 0xffffffff
+__device__ __forceinline__ void fr_from_mont(uint32_t *s) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t m = 0u - s[0];  // s[0]·0xffffffff
+        uint64_t c = ((uint64_t)m * FR_MOD[0] + s[0]) >> 32;
+#pragma unroll
+        for (int j = 1; j < 8; j++) {
+            c += (uint64_t)m * FR_MOD[j] + s[j];
+            s[j - 1] = (uint32_t)c;
+            c >>= 32;
+        }
+        s[7] = (uint32_t)c;
+    }
+    if (fr_geq_r(s)) fr_sub_r(s);
+}
+
+// c+1 bits of s starting at bit `lo` (lo ≥ -1; bits outside [0,256) read as 0)
+__device__ __forceinline__ uint32_t scalar_bits(const uint32_t *s, int lo, int cnt) {
+    uint32_t mask = (1u << cnt) - 1;
+    if (lo < 0) return (s[0] << 1) & mask;
+    int w = lo >> 5, sh = lo & 31;
+    uint64_t v = s[w];
+    if (w + 1 < 8) v |= (uint64_t)s[w + 1] << 32;
+    return (uint32_t)(v >> sh) & mask;
+}
+// Booth-recoded signed digit of window w: u + b[wc-1] − 2^c·b[wc+c-1] ∈ [−2^(c-1), 2^(c-1)].
+// Each window is independent of the others (no sequential carry), Σ d_w·2^(wc) = s for s < 2^255.
+__device__ __forceinline__ int booth_digit(const uint32_t *s, int w, int c) {
+    uint32_t v = scalar_bits(s, w * c - 1, c + 1);
+    int d = (int)((v >> 1) & ((1u << c) - 1)) + (int)(v & 1);
+    if ((v >> c) & 1) d -= (1 << c);
+    return d;
+}
+
+__device__ __forceinline__ void load_scalar(uint32_t *s, const uint32_t *scalars, size_t i, int mont) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(scalars + 8 * i);
+    uint4 a = p[0], b = p[1];
+    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
+    s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+    if (mont) fr_from_mont(s);
+    else { if (fr_geq_r(s)) fr_sub_r(s); if (fr_geq_r(s)) fr_sub_r(s); }  // 2^256 < 3r
+}
+
+}  // namespace b200msm

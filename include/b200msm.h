@@ -1,0 +1,123 @@
+/* b200msm — C-ABI of the B200-native BLS12-381 multi-scalar-multiplication engine.
+ *
+ * This is the drop-in boundary behind ark-blst's arkworks surface.  It replaces, wholesale,
+ *      crate::gpu::msm::<G>(bases, exponents)                reference src/gpu.rs:226-241
+ *      SingleMultiexpKernel::{create, multiexp}              reference src/gpu.rs:101-119,126-210
+ *      the ec-gpu-gen generated *_multiexp kernels           reference build.rs:9-12, gpu.rs:165-183
+ * and is what the two trait impls call instead:
+ *      <G1Projective as VariableBaseMSM>::msm / msm_bigint   reference src/g1.rs:621-632
+ *      <G2Projective as VariableBaseMSM>::msm / msm_bigint   reference src/g2.rs:601-612
+ * (INTEGRATION.md shows the Rust `extern "C"` block and the patched bodies.)
+ *
+ * Data layouts are the reference's own, passed as raw pointers with no conversion
+ * (#[repr(transparent)] newtypes over blst types, src/g1.rs:54-56,435-437, src/g2.rs:66-68,415-417):
+ *   G1 base   = blst_p1_affine : x, y          each 6×u64 LE Montgomery (R=2^384)   96 bytes
+ *   G2 base   = blst_p2_affine : x.c0,x.c1,y.c0,y.c1                                192 bytes
+ *   identity base = all-zero bytes (accepted; contributes nothing)
+ *   scalar    = 4×u64 LE; Montgomery Fr (R=2^256) when scalars_are_montgomery != 0 — the
+ *               &[Scalar] the trait's `msm` receives (src/scalar.rs:23-25) — else a plain
+ *               integer < 2^256 (reduced mod r on the device) — the &[BigInt<4>] of `msm_bigint`
+ *               and of the reference GPU arm (src/g1.rs:624-627)
+ *   G1 result = blst_p1 : X, Y, Z Jacobian Montgomery, 18×u64 (identity ⇔ Z = 0)    144 bytes
+ *   G2 result = blst_p2 : 36×u64                                                    288 bytes
+ * The result is Σ sᵢ·Pᵢ (the definition pinned by reference src/tests.rs:58-67); it equals the
+ * blst-backed value as a group element, i.e. after normalisation to affine.
+ *
+ * Error convention: every function returns 0 on success, a negative B200MSM_E* code otherwise;
+ * nothing throws or aborts across the boundary.  The Rust shim maps non-zero → Err(0), the
+ * reference GPU arm's convention (src/g1.rs:628-630).  b200msm_last_error() gives a thread-local
+ * message.  There is no CPU fallback: without a usable sm_100 device every call fails.
+ *
+ * Threading: all entry points may be called concurrently from any host thread (arkworks provers
+ * call msm from rayon workers); calls on the same device are serialised internally.
+ */
+#ifndef B200MSM_H
+#define B200MSM_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MSM_OK 0
+#define B200MSM_ENODEV (-1)   /* no CUDA device / not sm_100 */
+#define B200MSM_ECUDA (-2)    /* CUDA runtime error (message in b200msm_last_error) */
+#define B200MSM_EINVAL (-3)   /* bad argument */
+#define B200MSM_ENOMEM (-4)   /* device or host allocation failed */
+#define B200MSM_ENCCL (-5)    /* NCCL error on the multi-GPU path */
+
+#define B200MSM_G1 0
+#define B200MSM_G2 1
+
+/* Bind the engine to `n_devices` GPUs (0 = all visible) starting at `first_device`.  Optional:
+ * the first MSM call initialises with (0, current device only = 1).  Replaces Device::all() +
+ * program!(device) + SingleMultiexpKernel::create, which the reference repeats on every call
+ * (src/gpu.rs:233-237); here it happens once per process. */
+int b200msm_init(int first_device, int n_devices);
+void b200msm_shutdown(void);
+int b200msm_device_count(void);          /* devices bound by init */
+const char *b200msm_last_error(void);
+const char *b200msm_version(void);
+
+/* One-shot MSM on HOST buffers: copies bases and scalars to the device(s), runs, returns the
+ * Jacobian result in `out`.  Direct replacement of crate::gpu::msm (src/gpu.rs:226-241). */
+int b200msm_g1(const uint64_t *bases, const uint64_t *scalars, size_t n,
+               int scalars_are_montgomery, uint64_t out[18]);
+int b200msm_g2(const uint64_t *bases, const uint64_t *scalars, size_t n,
+               int scalars_are_montgomery, uint64_t out[36]);
+
+/* Resident bases: upload a proving key's bases once — sharded evenly by index
+ * range across the bound devices — then run many scalar vectors against them. */
+typedef struct b200msm_bases b200msm_bases; /* opaque */
+int b200msm_bases_upload(int group /*B200MSM_G1|G2*/, const uint64_t *bases, size_t n,
+                         b200msm_bases **handle);
+int b200msm_bases_free(b200msm_bases *handle);
+/* scalars on the host; n must not exceed the uploaded count (prefix is used) */
+int b200msm_run(const b200msm_bases *handle, const uint64_t *scalars, size_t n,
+                int scalars_are_montgomery, uint64_t *out /*18 or 36 u64*/);
+
+/* Device-pointer form for callers that already hold the inputs in HBM on the CURRENT device
+ * (bench.py's kernel-only figure; torch tensors via data_ptr()).  `d_out` is a device buffer of
+ * 18/36 u64; the call is asynchronous on `stream` (a cudaStream_t, 0 = default). */
+int b200msm_run_device(int group, const void *d_bases, const void *d_scalars, size_t n,
+                       int scalars_are_montgomery, void *d_out, void *stream);
+/* d_out = Σ of `count` Jacobian partials at d_partials (the final addition after the NCCL
+ * gather of per-GPU partial sums); asynchronous on `stream`. */
+int b200msm_sum_partials_device(int group, const void *d_partials, int count, void *d_out,
+                                void *stream);
+
+/* Tunables (SURVEY §5 "config/flags"): window width c; 0 = automatic from n. */
+int b200msm_set_window_bits(int c);
+/* Per-phase device times (ms) of the most recent MSM on this thread's device:
+ * [0] digits [1] sort [2] bucket bounds+order [3] accumulate [4] reduce [5] combine [6] total
+ * [7] accumulate launches. Filled only when b200msm_set_profiling(1). */
+int b200msm_set_profiling(int on);
+int b200msm_last_phase_ms(double out[8]);
+
+/* ---- synthetic data + measurement utilities (bench / tests; not on the reference's path) ---- */
+/* Pᵢ = kᵢ·G with kᵢ the counter-based stream of oracle/bls12381.py::synth_dlog, written as
+ * affine Montgomery limbs into device memory. */
+int b200msm_synth_bases_device(int group, uint64_t seed, size_t n, void *d_out, void *stream);
+/* sᵢ of oracle/bls12381.py::synth_scalar (canonical or Montgomery) into device memory */
+int b200msm_synth_scalars_device(uint64_t seed, size_t n, int montgomery, void *d_out, void *stream);
+/* Measured 32-bit IMAD issue rate of the current device, in IMAD/s (the roofline denominator;
+ * MEASURED_PEAKS.json has no integer figure). out[0]=mad.lo rate, out[1]=fused lo/hi
+ * (IMAD.WIDE) carry-chain rate ×2, out[2]=SM clock estimate in MHz during the run. */
+int b200msm_imad_peak(double out[3]);
+
+/* ---- unit hooks used by the parity tests (element-wise, device-side, host buffers) ---- */
+/* op: 0 mul, 1 add, 2 sub, 3 sqr(b ignored), 4 neg(b ignored), 5 inv(b ignored).
+ * a, b, out: n elements of 6 (Fp) or 12 (Fp2) u64 each. */
+int b200msm_dbg_field_op(int fp2, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+/* op: 0 madd (acc XYZZ + affine), 1 add (XYZZ + XYZZ), 2 dbl (XYZZ); results as XYZZ→Jacobian.
+ * acc: n×4 field elems, q: n×(2|4) field elems, out: n×3 field elems (Jacobian). */
+int b200msm_dbg_point_op(int group, int op, const uint64_t *acc, const uint64_t *q, uint64_t *out, size_t n);
+/* signed window digits of host scalars exactly as the digit kernel emits them:
+ * out[w*n + i] = digit (int32) for w < nwin. */
+int b200msm_dbg_digits(const uint64_t *scalars, size_t n, int montgomery, int c, int32_t *out, int *nwin);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -12,8 +12,8 @@ cargo/rustc).  This oracle therefore follows
         Fp modulus limbs                 src/fp.rs:25-32
         (p-1)/2 limbs (the only KAT)     src/fp.rs:714-721
         Fr modulus limbs                 src/scalar.rs:476-481
-        G1 cofactor                      src/g1.rs:41
-        G2 cofactor                      src/g2.rs:46-55
+        G1 cofactor                      src/g1.rs:42
+        G2 cofactor                      src/g2.rs:45-54
   * the reference's data layouts: Fp = 6×u64 LE Montgomery (R=2^384)  src/fp.rs:482-491,532;
     Fp2 = (c0,c1) src/fp2.rs:450-454; Scalar = 4×u64 LE Montgomery (R=2^256) src/scalar.rs:23-25;
     G1Affine/G1Projective are repr(transparent) over blst_p1_affine / blst_p1
@@ -58,8 +58,8 @@ FR_MONT_RINV = pow(FR_MONT_R, -1, R_ORDER)
 P_INV64 = (-pow(P, -1, 1 << 64)) % (1 << 64)   # 0x89f3fffcfffcfffd
 R_INV64 = (-pow(R_ORDER, -1, 1 << 64)) % (1 << 64)
 
-G1_COFACTOR = limbs_to_int([0x8C00AAAB0000AAAB, 0x396C8C005555E156])  # src/g1.rs:41
-G2_COFACTOR = limbs_to_int([  # src/g2.rs:46-55
+G1_COFACTOR = limbs_to_int([0x8C00AAAB0000AAAB, 0x396C8C005555E156])  # src/g1.rs:42
+G2_COFACTOR = limbs_to_int([  # src/g2.rs:45-54
     0xCF1C38E31C7238E5, 0x1616EC6E786F0C70, 0x21537E293A6691AE, 0xA628F1CB4D9E82EF,
     0xA68A205B2E5A7DDF, 0xCD91DE4547085ABA, 0x91D50792876A202, 0x5D543A95414E7F1,
 ])
