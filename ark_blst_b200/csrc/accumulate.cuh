@@ -1,23 +1,41 @@
-// Bucket accumulation kernel (template over the field; instantiated per group in its own TU).
+// Bucket accumulation (template over the field; instantiated per group in its own TU).
+//
+// Light buckets (≤ `heavy_thr` entries — everything a uniform scalar distribution produces) take
+// one thread each, in decreasing-size order so the lanes of a warp run the same trip count.
+// Heavy buckets — the degenerate top window when c does not divide 255 evenly, or the digit-1
+// bucket of witness-like scalars full of ones — are cut into block-sized tasks whose partial sums
+// are tree-reduced in shared memory and then folded per bucket; task lists and counts live in
+// device memory, so no host round trip is needed to size that work.
 #pragma once
 #include "ec.cuh"
 
 namespace b200msm {
 
-// ---- bucket accumulation: the hot kernel ---------------------------------------------------
-// One thread per bucket, buckets taken in decreasing-size order so the lanes of a warp run the
-// same trip count.  Accumulator in XYZZ, points read as 16-byte vectors in the reference's affine
-// layout, sign applied to y on the fly.
+struct HeavyHeader {
+    uint32_t n_heavy;  // heavy buckets
+    uint32_t n_tasks;  // block tasks over all heavy buckets
+};
+struct HeavyBucket {
+    uint32_t bucket, task_base, n_tasks;
+};
+struct HeavyTask {
+    uint32_t offset, len;  // slice of the sorted value array
+};
+
+// ---- light buckets: the hot kernel -----------------------------------------------------------
+// Accumulator in XYZZ, points read as 16-byte vectors in the reference's affine layout, sign
+// applied to y on the fly.
 template <class F>
 __global__ void __launch_bounds__(128)
 k_accumulate(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ vals,
              const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, uint32_t nb,
-             uint32_t *__restrict__ buckets) {
+             uint32_t heavy_thr, uint32_t *__restrict__ buckets) {
     constexpr int W = field_words<F>::value;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nb) return;
     uint32_t b = order[t];
     uint32_t s = start[b], e = start[b + 1];
+    if (e - s > heavy_thr) return;  // written by k_heavy_final
     xyzz<F> acc;
     xyzz_set_inf(acc);
     for (uint32_t j = s; j < e; j++) {
@@ -31,6 +49,91 @@ k_accumulate(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ va
         xyzz_madd(acc, x, y);
     }
     xyzz_store(buckets + (size_t)b * (4 * W), acc);
+}
+
+// ---- heavy buckets ---------------------------------------------------------------------------
+// one thread per bucket rank: heavy ones claim a slot and a run of tasks of ≤ chunk entries
+static __global__ void __launch_bounds__(256)
+k_plan_heavy(const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, uint32_t nb, uint32_t heavy_thr,
+             uint32_t chunk, HeavyHeader *__restrict__ hdr, HeavyBucket *__restrict__ hb, HeavyTask *__restrict__ tasks) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb) return;
+    uint32_t b = order[t];
+    uint32_t s = start[b], cnt = start[b + 1] - s;
+    if (cnt <= heavy_thr) return;
+    uint32_t nt = (cnt + chunk - 1) / chunk;
+    uint32_t slot = atomicAdd(&hdr->n_heavy, 1u);
+    uint32_t base = atomicAdd(&hdr->n_tasks, nt);
+    hb[slot] = HeavyBucket{b, base, nt};
+    for (uint32_t k = 0; k < nt; k++) {
+        uint32_t off = k * chunk;
+        tasks[base + k] = HeavyTask{s + off, cnt - off < chunk ? cnt - off : chunk};
+    }
+}
+
+// block tree-sum of one XYZZ value per thread through shared memory; result in thread 0's `acc`
+template <class F, int THREADS>
+__device__ __forceinline__ void block_tree_sum(xyzz<F> &acc, uint32_t *smem) {
+    constexpr int PW = 4 * field_words<F>::value;
+    for (int stride = THREADS / 2; stride >= 1; stride >>= 1) {
+        if ((int)threadIdx.x >= stride && (int)threadIdx.x < 2 * stride) xyzz_store(smem + (size_t)(threadIdx.x - stride) * PW, acc);
+        __syncthreads();
+        if ((int)threadIdx.x < stride) {
+            xyzz<F> o;
+            xyzz_load(o, smem + (size_t)threadIdx.x * PW);
+            xyzz_add_ni(acc, o);
+        }
+        __syncthreads();
+    }
+}
+
+// grid-stride over tasks: each block sums ≤ chunk points into one partial
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_heavy_tasks(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ vals,
+              const HeavyHeader *__restrict__ hdr, const HeavyTask *__restrict__ tasks, uint32_t *__restrict__ partials) {
+    constexpr int W = field_words<F>::value;
+    constexpr int PW = 4 * W;
+    __shared__ __align__(16) uint32_t smem[(THREADS / 2) * PW];
+    const uint32_t nt = hdr->n_tasks;
+    for (uint32_t t = blockIdx.x; t < nt; t += gridDim.x) {
+        HeavyTask tk = tasks[t];
+        xyzz<F> acc;
+        xyzz_set_inf(acc);
+        for (uint32_t j = threadIdx.x; j < tk.len; j += THREADS) {
+            uint32_t v = vals[tk.offset + j];
+            const uint32_t *p = bases + (size_t)(v & 0x7fffffffu) * (2 * W);
+            F x, y;
+            f_load(x, p);
+            f_load(y, p + W);
+            if (f_is_zero(x) && f_is_zero(y)) continue;
+            f_cneg(y, y, v >> 31);
+            xyzz_madd_ni(acc, x, y);
+        }
+        block_tree_sum<F, THREADS>(acc, smem);
+        if (threadIdx.x == 0) xyzz_store(partials + (size_t)t * PW, acc);
+    }
+}
+
+// grid-stride over heavy buckets: each block folds the bucket's task partials into the bucket
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_heavy_final(const HeavyHeader *__restrict__ hdr, const HeavyBucket *__restrict__ hb,
+              const uint32_t *__restrict__ partials, uint32_t *__restrict__ buckets) {
+    constexpr int PW = 4 * field_words<F>::value;
+    __shared__ __align__(16) uint32_t smem[(THREADS / 2) * PW];
+    const uint32_t nh = hdr->n_heavy;
+    for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
+        HeavyBucket B = hb[h];
+        xyzz<F> acc, o;
+        xyzz_set_inf(acc);
+        for (uint32_t k = threadIdx.x; k < B.n_tasks; k += THREADS) {
+            xyzz_load(o, partials + (size_t)(B.task_base + k) * PW);
+            xyzz_add_ni(acc, o);
+        }
+        if (B.n_tasks > 1) block_tree_sum<F, THREADS>(acc, smem);  // block-uniform condition
+        if (threadIdx.x == 0) xyzz_store(buckets + (size_t)B.bucket * PW, acc);
+    }
 }
 
 }  // namespace b200msm

@@ -19,6 +19,10 @@
 
 using namespace b200msm;
 
+namespace b200msm {
+unsigned long long g_own_launches = 0;
+}
+
 namespace {
 
 thread_local std::string g_err;
@@ -85,12 +89,15 @@ struct DeviceCtx {
     std::mutex mu;
     cudaStream_t stream = nullptr;
     DevBuf bases, scalars, keys[2], vals[2], cubtmp, start, cnt[2], ord[2], buckets, lvlR[2], lvlC[2], out;
+    DevBuf hvy_hdr, hvy_buckets, hvy_tasks, hvy_partials;
     cudaEvent_t ev[8] = {};
     double phase_ms[8] = {};
+    bool phase_pending = false;
     int sm_count = 0;
     void release_all() {
         for (DevBuf *b : {&bases, &scalars, &keys[0], &keys[1], &vals[0], &vals[1], &cubtmp, &start, &cnt[0], &cnt[1],
-                          &ord[0], &ord[1], &buckets, &lvlR[0], &lvlR[1], &lvlC[0], &lvlC[1], &out})
+                          &ord[0], &ord[1], &buckets, &lvlR[0], &lvlR[1], &lvlC[0], &lvlC[1], &out, &hvy_hdr, &hvy_buckets,
+                          &hvy_tasks, &hvy_partials})
             b->release();
     }
 };
@@ -184,6 +191,15 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_sca
     }
     if (int rc = cx.start.reserve(((size_t)pl.nb + 2) * 4)) return rc;
     if (int rc = cx.buckets.reserve((size_t)pl.nb * PB)) return rc;
+    // heavy buckets: more than 3× the mean occupancy of a window's buckets (never reached by a
+    // uniform distribution); worst-case list sizes follow from Σ counts = m
+    const uint32_t avg = (uint32_t)((n + pl.nbw - 1) / pl.nbw);
+    const uint32_t heavy_thr = std::max<uint32_t>(32, 3 * avg);
+    const size_t max_heavy = m / (heavy_thr + 1) + 1, max_tasks = m / HEAVY_CHUNK + max_heavy + 1;
+    if (int rc = cx.hvy_hdr.reserve(16)) return rc;
+    if (int rc = cx.hvy_buckets.reserve(max_heavy * 12)) return rc;
+    if (int rc = cx.hvy_tasks.reserve(max_tasks * 8)) return rc;
+    if (int rc = cx.hvy_partials.reserve(max_tasks * PB)) return rc;
     uint32_t *keys[2] = {cx.keys[0].as<uint32_t>(), cx.keys[1].as<uint32_t>()};
     uint32_t *vals[2] = {cx.vals[0].as<uint32_t>(), cx.vals[1].as<uint32_t>()};
     uint32_t *cnt[2] = {cx.cnt[0].as<uint32_t>(), cx.cnt[1].as<uint32_t>()};
@@ -210,7 +226,12 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_sca
     CUDA_TRY(sort_pairs(cx.cubtmp.p, &tmp2, cnt[0], cnt[1], ord[0], ord[1], pl.nb, cnt_bits, true, &osel, st));
     mark();
     // 4. bucket accumulation
-    (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals[sel], start, ord[osel], pl.nb, cx.buckets.as<uint32_t>(), st);
+    CUDA_TRY(cudaMemsetAsync(cx.hvy_hdr.p, 0, 16, st));
+    (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals[sel], start, ord[osel], pl.nb, heavy_thr,
+                                                       cx.buckets.as<uint32_t>(), st);
+    (g2 ? launch_heavy_g2 : launch_heavy_g1)(d_bases, vals[sel], start, ord[osel], pl.nb, heavy_thr, cx.hvy_hdr.p,
+                                             cx.hvy_buckets.p, cx.hvy_tasks.p, cx.hvy_partials.as<uint32_t>(),
+                                             cx.buckets.as<uint32_t>(), cx.sm_count * 4, st);
     mark();
     // 5. per-window weighted bucket sums, by levels
     const uint32_t *X = cx.buckets.as<uint32_t>();
@@ -234,17 +255,7 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_sca
     (g2 ? launch_combine_g2 : launch_combine_g1)(Cin, X, pl.nwin, pl.c, d_out, st);
     mark();
     CUDA_TRY(cudaGetLastError());
-    if (prof) {
-        CUDA_TRY(cudaStreamSynchronize(st));
-        float ms;
-        for (int i = 0; i < 6; i++) {
-            cudaEventElapsedTime(&ms, cx.ev[i], cx.ev[i + 1]);
-            cx.phase_ms[i] = ms;
-        }
-        cudaEventElapsedTime(&ms, cx.ev[0], cx.ev[6]);
-        cx.phase_ms[6] = ms;
-        cx.phase_ms[7] = 1;
-    }
+    cx.phase_pending = prof;  // elapsed times are read lazily by b200msm_last_phase_ms (no sync here)
     return 0;
 }
 
@@ -446,6 +457,8 @@ int b200msm_sum_partials_device(int group, const void *d_partials, int count, vo
     return 0;
 }
 
+unsigned long long b200msm_launch_count(void) { return __atomic_load_n(&g_own_launches, __ATOMIC_RELAXED); }
+
 int b200msm_set_window_bits(int c) {
     if (c < 0 || c == 1 || c > 24) return fail(B200MSM_EINVAL, "window bits must be 0 (auto) or 2..24");
     g_eng.window_override = c;
@@ -459,6 +472,19 @@ int b200msm_last_phase_ms(double out[8]) {
     if (!g_eng.inited) return fail(B200MSM_EINVAL, "engine not initialised");
     DeviceCtx *cx = ctx_for_current_device();
     if (!cx) cx = g_eng.ctx[0].get();
+    std::lock_guard<std::mutex> lk(cx->mu);
+    if (cx->phase_pending) {
+        CUDA_TRY(cudaEventSynchronize(cx->ev[6]));
+        float ms;
+        for (int i = 0; i < 6; i++) {
+            CUDA_TRY(cudaEventElapsedTime(&ms, cx->ev[i], cx->ev[i + 1]));
+            cx->phase_ms[i] = ms;
+        }
+        CUDA_TRY(cudaEventElapsedTime(&ms, cx->ev[0], cx->ev[6]));
+        cx->phase_ms[6] = ms;
+        cx->phase_ms[7] = 1;
+        cx->phase_pending = false;
+    }
     memcpy(out, cx->phase_ms, sizeof cx->phase_ms);
     return 0;
 }

@@ -80,6 +80,15 @@ __device__ __forceinline__ void f_inv(fp2 &r, const fp2 &a) {
     fp_neg(r.c1, t);
 }
 
+// word accessors with compile-time indices (keep everything in registers under full unrolling)
+__device__ __forceinline__ uint32_t f_word(const fp &a, int i) { return a.l[i]; }
+__device__ __forceinline__ void f_set_word(fp &a, int i, uint32_t v) { a.l[i] = v; }
+__device__ __forceinline__ uint32_t f_word(const fp2 &a, int i) { return i < 12 ? a.c0.l[i] : a.c1.l[i - 12]; }
+__device__ __forceinline__ void f_set_word(fp2 &a, int i, uint32_t v) {
+    if (i < 12) a.c0.l[i] = v;
+    else a.c1.l[i - 12] = v;
+}
+
 template <class F> struct field_words;
 template <> struct field_words<fp> { static constexpr int value = 12; };   // u32 words per element
 template <> struct field_words<fp2> { static constexpr int value = 24; };

@@ -59,15 +59,19 @@ k_counts(const uint32_t *__restrict__ start, uint32_t nb, uint32_t clampv,
 
 void launch_digits(const uint32_t *scalars, size_t n, int mont, int c, int nwin, uint32_t *keys, uint32_t *vals,
                    cudaStream_t st) {
+    count_launch();
     k_digits<<<blocks_for(n, 256), 256, 0, st>>>(scalars, n, mont, c, nwin, keys, vals);
 }
 void launch_digits_dbg(const uint32_t *scalars, size_t n, int mont, int c, int nwin, int *out, cudaStream_t st) {
+    count_launch();
     k_digits_dbg<<<blocks_for(n, 256), 256, 0, st>>>(scalars, n, mont, c, nwin, out);
 }
 void launch_bounds(const uint32_t *keys, size_t m, uint32_t nb, uint32_t *start, cudaStream_t st) {
+    count_launch();
     k_bounds<<<blocks_for(m + 1, 256), 256, 0, st>>>(keys, m, nb, start);
 }
 void launch_counts(const uint32_t *start, uint32_t nb, uint32_t clampv, uint32_t *cnt, uint32_t *ids, cudaStream_t st) {
+    count_launch();
     k_counts<<<blocks_for(nb, 256), 256, 0, st>>>(start, nb, clampv, cnt, ids);
 }
 cudaError_t sort_pairs(void *tmp, size_t *tmp_bytes, uint32_t *k0, uint32_t *k1, uint32_t *v0, uint32_t *v1, size_t m,

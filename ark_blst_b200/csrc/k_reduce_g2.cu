@@ -5,13 +5,16 @@
 namespace b200msm {
 void launch_wsum_level_g2(const uint32_t *X, const uint32_t *Cin, uint32_t len, uint32_t m, int log2M, uint32_t nwin,
                           uint32_t *Rout, uint32_t *Cout, cudaStream_t st) {
+    count_launch();
     uint32_t nseg = len / m;
-    k_wsum_level<fp2><<<blocks_for((size_t)nseg * nwin, 128), 128, 0, st>>>(X, Cin, len, m, log2M, nwin, Rout, Cout);
+    k_wsum_level<fp2><<<blocks_for((size_t)nseg * nwin * 4, 128), 128, 0, st>>>(X, Cin, len, m, log2M, nwin, Rout, Cout);
 }
 void launch_combine_g2(const uint32_t *C, const uint32_t *R, int nwin, int c, uint32_t *out, cudaStream_t st) {
+    count_launch();
     k_combine<fp2><<<1, 32, 0, st>>>(C, R, nwin, c, out);
 }
 void launch_sum_partials_g2(const uint32_t *partials, int count, uint32_t *out, cudaStream_t st) {
+    count_launch();
     k_sum_partials<fp2><<<1, 32, 0, st>>>(partials, count, out);
 }
 }  // namespace b200msm

@@ -20,10 +20,18 @@ cudaError_t sort_pairs(void *tmp, size_t *tmp_bytes, uint32_t *k0, uint32_t *k1,
                        int end_bit, bool descending, int *sel, cudaStream_t st);
 
 // k_accumulate_g{1,2}.cu
+constexpr uint32_t HEAVY_CHUNK = 4096;  // entries per block task of a heavy bucket
 void launch_accumulate_g1(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
-                          uint32_t nb, uint32_t *buckets, cudaStream_t st);
+                          uint32_t nb, uint32_t heavy_thr, uint32_t *buckets, cudaStream_t st);
 void launch_accumulate_g2(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
-                          uint32_t nb, uint32_t *buckets, cudaStream_t st);
+                          uint32_t nb, uint32_t heavy_thr, uint32_t *buckets, cudaStream_t st);
+// plan + block tasks + per-bucket fold for buckets above heavy_thr; hdr must be zeroed (8 bytes)
+void launch_heavy_g1(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
+                     uint32_t nb, uint32_t heavy_thr, void *hdr, void *hb, void *tasks, uint32_t *partials,
+                     uint32_t *buckets, int grid, cudaStream_t st);
+void launch_heavy_g2(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
+                     uint32_t nb, uint32_t heavy_thr, void *hdr, void *hb, void *tasks, uint32_t *partials,
+                     uint32_t *buckets, int grid, cudaStream_t st);
 
 // k_reduce_g{1,2}.cu
 void launch_wsum_level_g1(const uint32_t *X, const uint32_t *Cin, uint32_t len, uint32_t m, int log2M, uint32_t nwin,
@@ -43,6 +51,10 @@ void launch_imad_peak(int mode, int blocks, int threads, uint32_t *buf, int iter
 void launch_dbg_field_op(int is_fp2, int op, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n);
 void launch_dbg_point_op_g1(int op, const uint32_t *acc, const uint32_t *q, uint32_t *out, size_t n);
 void launch_dbg_point_op_g2(int op, const uint32_t *acc, const uint32_t *q, uint32_t *out, size_t n);
+
+// number of this library's own kernel launches since load (bench.py reports the per-step count)
+extern unsigned long long g_own_launches;
+inline void count_launch() { __atomic_fetch_add(&g_own_launches, 1ull, __ATOMIC_RELAXED); }
 
 inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 

@@ -1,0 +1,98 @@
+// C++ mirror of the reference's arkworks surface for the MSM path (the reference's host language,
+// Rust, has no toolchain in this image; rust/gpu.rs holds the same shim as Rust text).
+//
+// Mirrors, name for name:
+//   impl VariableBaseMSM for G1Projective { fn msm(bases, scalars) -> Result<Self, usize> }
+//                                                         reference src/g1.rs:602-632
+//   impl VariableBaseMSM for G2Projective                  reference src/g2.rs:582-612
+//   msm_bigint / msm_unchecked                             arkworks defaults the new build overrides
+//   ScalarMul::{MulBase, NEGATION_IS_CHEAP}                reference src/g1.rs:593-600
+// Types are the reference's #[repr(transparent)] layouts (src/g1.rs:54-56,435-437,
+// src/g2.rs:66-68,415-417, src/scalar.rs:23-25): plain limb arrays, passed by pointer, no copies.
+// Header-only; link with -lb200msm.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+#include "../../include/b200msm.h"
+
+namespace ark_blst {
+
+using usize = std::size_t;
+
+struct Scalar { uint64_t l[4]; };        // Montgomery Fr (blstrs::Scalar)
+struct BigInt4 { uint64_t l[4]; };       // ark_ff::BigInt<4>, canonical little-endian
+struct G1Affine { uint64_t l[12]; };     // blst_p1_affine
+struct G2Affine { uint64_t l[24]; };     // blst_p2_affine
+static_assert(sizeof(Scalar) == 32 && sizeof(BigInt4) == 32, "scalar layout");
+static_assert(sizeof(G1Affine) == 96 && sizeof(G2Affine) == 192, "affine layout");
+
+// Result<T, usize>
+template <class T> struct Result {
+    bool ok;
+    T value;
+    usize err;
+    bool is_ok() const { return ok; }
+    bool is_err() const { return !ok; }
+    const T &unwrap() const {
+        if (!ok) throw std::string("called unwrap() on Err(") + std::to_string(err) + ")";
+        return value;
+    }
+    usize unwrap_err() const { return err; }
+    static Result Ok(const T &v) { return Result{true, v, 0}; }
+    static Result Err(usize e) { return Result{false, T{}, e}; }
+};
+
+namespace detail {
+template <class Proj, class Aff>
+Result<Proj> call(int (*f)(const uint64_t *, const uint64_t *, size_t, int, uint64_t *), const Aff *bases, usize nb,
+                  const uint64_t *scalars, usize ns, int mont) {
+    if (nb != ns) return Result<Proj>::Err(nb < ns ? nb : ns);   // arkworks: Err(min(len))
+    Proj out{};
+    int rc = f(reinterpret_cast<const uint64_t *>(bases), scalars, nb, mont, out.l);
+    if (rc != 0) return Result<Proj>::Err(0);                      // reference GPU arm: Err(0), src/g1.rs:628-630
+    return Result<Proj>::Ok(out);
+}
+}  // namespace detail
+
+struct G1Projective {                    // blst_p1 (Jacobian)
+    uint64_t l[18];
+    using MulBase = G1Affine;
+    static constexpr bool NEGATION_IS_CHEAP = true;
+    bool is_zero() const { for (int i = 12; i < 18; i++) if (l[i]) return false; return true; }
+
+    static Result<G1Projective> msm(const G1Affine *bases, usize nb, const Scalar *scalars, usize ns) {
+        return detail::call<G1Projective>(b200msm_g1, bases, nb, reinterpret_cast<const uint64_t *>(scalars), ns, 1);
+    }
+    static G1Projective msm_bigint(const G1Affine *bases, usize nb, const BigInt4 *bigints, usize ns) {
+        usize n = nb < ns ? nb : ns;     // infallible and truncating, like arkworks' msm_bigint
+        return detail::call<G1Projective>(b200msm_g1, bases, n, reinterpret_cast<const uint64_t *>(bigints), n, 0).unwrap();
+    }
+    static G1Projective msm_unchecked(const G1Affine *bases, usize nb, const Scalar *scalars, usize ns) {
+        usize n = nb < ns ? nb : ns;
+        return msm(bases, n, scalars, n).unwrap();
+    }
+};
+
+struct G2Projective {                    // blst_p2 (Jacobian)
+    uint64_t l[36];
+    using MulBase = G2Affine;
+    static constexpr bool NEGATION_IS_CHEAP = true;
+    bool is_zero() const { for (int i = 24; i < 36; i++) if (l[i]) return false; return true; }
+
+    static Result<G2Projective> msm(const G2Affine *bases, usize nb, const Scalar *scalars, usize ns) {
+        return detail::call<G2Projective>(b200msm_g2, bases, nb, reinterpret_cast<const uint64_t *>(scalars), ns, 1);
+    }
+    static G2Projective msm_bigint(const G2Affine *bases, usize nb, const BigInt4 *bigints, usize ns) {
+        usize n = nb < ns ? nb : ns;
+        return detail::call<G2Projective>(b200msm_g2, bases, n, reinterpret_cast<const uint64_t *>(bigints), n, 0).unwrap();
+    }
+    static G2Projective msm_unchecked(const G2Affine *bases, usize nb, const Scalar *scalars, usize ns) {
+        usize n = nb < ns ? nb : ns;
+        return msm(bases, n, scalars, n).unwrap();
+    }
+};
+static_assert(sizeof(G1Projective) == 144 && sizeof(G2Projective) == 288, "projective layout");
+
+}  // namespace ark_blst

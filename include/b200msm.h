@@ -87,6 +87,9 @@ int b200msm_run_device(int group, const void *d_bases, const void *d_scalars, si
 int b200msm_sum_partials_device(int group, const void *d_partials, int count, void *d_out,
                                 void *stream);
 
+/* Cumulative count of this library's own kernel launches (CUB sort kernels excluded). */
+unsigned long long b200msm_launch_count(void);
+
 /* Tunables (SURVEY §5 "config/flags"): window width c; 0 = automatic from n. */
 int b200msm_set_window_bits(int c);
 /* Per-phase device times (ms) of the most recent MSM on this thread's device:

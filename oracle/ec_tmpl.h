@@ -186,3 +186,65 @@ static void EC(tile)(EC(xyzz_t) * out, EC(xyzz_t) * buckets, const EC(aff_t) * b
     }
     *out = acc;
 }
+
+/* ---- fast synthetic bases: k·G by an 8-bit fixed-base table + batched normalisation -------- */
+/* out[i] = affine(in[i]) for XYZZ inputs, one field inversion per call (Montgomery's trick).
+ * x = X/ZZ, y = Y/ZZZ with 1/ZZ = ZZ²·(1/ZZZ)² since ZZ³ = ZZZ². */
+static void EC(batch_to_aff)(EC(aff_t) * out, const EC(xyzz_t) * in, size_t n, F *scratch) {
+    F acc = F_ONE;
+    for (size_t i = 0; i < n; i++) {
+        scratch[i] = acc;
+        if (!EC(xyzz_is_inf)(&in[i])) FN(mul)(&acc, &acc, &in[i].zzz);
+    }
+    F inv;
+    FN(inv)(&inv, &acc);
+    for (size_t i = n; i-- > 0;) {
+        if (EC(xyzz_is_inf)(&in[i])) { memset(&out[i], 0, sizeof out[i]); continue; }
+        F zi, t;
+        FN(mul)(&zi, &inv, &scratch[i]);      /* 1/ZZZ_i */
+        FN(mul)(&inv, &inv, &in[i].zzz);
+        FN(mul)(&out[i].y, &in[i].y, &zi);
+        FN(sqr)(&t, &zi);
+        FN(mul)(&t, &t, &in[i].zz);
+        FN(mul)(&t, &t, &in[i].zz);           /* 1/ZZ_i */
+        FN(mul)(&out[i].x, &in[i].x, &t);
+    }
+}
+/* table[j*255 + d-1] = d·2^(8j)·G, j < 32, 1 ≤ d ≤ 255 */
+static void EC(build_table)(EC(aff_t) * table, const EC(aff_t) * gen) {
+    size_t n = 32 * 255;
+    EC(xyzz_t) *t = (EC(xyzz_t) *)malloc(n * sizeof *t);
+    F *scratch = (F *)malloc(n * sizeof(F));
+    EC(xyzz_t) base;
+    EC(xyzz_set_inf)(&base);
+    EC(xyzz_madd)(&base, gen, 0);
+    for (int j = 0; j < 32; j++) {
+        EC(xyzz_t) acc = base;
+        for (int d = 1; d <= 255; d++) {
+            t[j * 255 + d - 1] = acc;
+            EC(xyzz_add)(&acc, &base);
+        }
+        for (int k = 0; k < 8; k++) EC(xyzz_dbl)(&base, &base);
+    }
+    EC(batch_to_aff)(table, t, n, scratch);
+    free(t);
+    free(scratch);
+}
+/* out[i - lo] for i in [lo, hi): k_i·G with k_i canonical little-endian bytes from `dlogs` */
+static void EC(fixed_base_range)(EC(aff_t) * out, const EC(aff_t) * table, const uint64_t *dlogs, size_t lo,
+                                 size_t hi) {
+    enum { CH = 512 };
+    EC(xyzz_t) buf[CH];
+    F scratch[CH];
+    for (size_t s = lo; s < hi; s += CH) {
+        size_t m = hi - s < CH ? hi - s : CH;
+        for (size_t i = 0; i < m; i++) {
+            const uint8_t *kb = (const uint8_t *)(dlogs + 4 * (s + i));
+            EC(xyzz_set_inf)(&buf[i]);
+            for (int j = 0; j < 32; j++)
+                if (kb[j]) EC(xyzz_madd)(&buf[i], &table[j * 255 + kb[j] - 1], 0);
+        }
+        EC(batch_to_aff)(out + (s - lo), buf, m, scratch);
+    }
+}
+

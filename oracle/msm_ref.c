@@ -332,47 +332,39 @@ API void ref_synth_dlogs(uint64_t seed, size_t n, uint64_t *out) {
 
 typedef struct {
     int g2;
-    uint64_t seed;
     size_t lo, hi;
     uint64_t *out;
-    const uint64_t *gen;
+    const void *table;
+    const uint64_t *dlogs;
 } synth_t;
 static void *synth_worker(void *arg) {
     synth_t *S = (synth_t *)arg;
-    for (size_t i = S->lo; i < S->hi; i++) {
-        uint64_t k[4];
-        fr_t s;
-        synth_scalar(S->seed ^ 0x5EEDBA5E5EEDBA5EULL, i, &s);
-        if (!(s.l[0] | s.l[1] | s.l[2] | s.l[3])) s.l[0] = 1;
-        memcpy(k, s.l, 32);
-        if (S->g2) {
-            g2_xyzz_t t;
-            g2_jac_t j;
-            g2_mul(&t, (const g2_aff_t *)S->gen, k);
-            g2_xyzz_to_jac(&j, &t);
-            g2_jac_to_aff((g2_aff_t *)(S->out + 24 * i), &j);
-        } else {
-            g1_xyzz_t t;
-            g1_jac_t j;
-            g1_mul(&t, (const g1_aff_t *)S->gen, k);
-            g1_xyzz_to_jac(&j, &t);
-            g1_jac_to_aff((g1_aff_t *)(S->out + 12 * i), &j);
-        }
-    }
+    if (S->g2)
+        g2_fixed_base_range((g2_aff_t *)(S->out + 24 * S->lo), (const g2_aff_t *)S->table, S->dlogs, S->lo, S->hi);
+    else
+        g1_fixed_base_range((g1_aff_t *)(S->out + 12 * S->lo), (const g1_aff_t *)S->table, S->dlogs, S->lo, S->hi);
     return NULL;
 }
-/* bases Pᵢ = kᵢ·G (gen passed in as Montgomery affine limbs by the caller) */
+/* bases Pᵢ = kᵢ·G (gen passed in as Montgomery affine limbs by the caller); kᵢ = ref_synth_dlogs */
 API void ref_synth_bases(int g2, uint64_t seed, size_t n, const uint64_t *gen, uint64_t *out,
                          int nthreads) {
+    if (n == 0) return;
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
+    uint64_t *dlogs = (uint64_t *)malloc(n * 32);
+    ref_synth_dlogs(seed, n, dlogs);
+    void *table = malloc(32 * 255 * (g2 ? sizeof(g2_aff_t) : sizeof(g1_aff_t)));
+    if (g2) g2_build_table((g2_aff_t *)table, (const g2_aff_t *)gen);
+    else g1_build_table((g1_aff_t *)table, (const g1_aff_t *)gen);
     pthread_t th[256];
     synth_t sj[256];
     for (int t = 0; t < nthreads; t++) {
-        sj[t] = (synth_t){g2, seed, n * t / nthreads, n * (t + 1) / nthreads, out, gen};
+        sj[t] = (synth_t){g2, n * t / nthreads, n * (t + 1) / nthreads, out, table, dlogs};
         pthread_create(&th[t], NULL, synth_worker, &sj[t]);
     }
     for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(table);
+    free(dlogs);
 }
 
 /* T2 oracle helper: Σ sᵢ·kᵢ mod r over the synthetic streams (canonical in, canonical out) */

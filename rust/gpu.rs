@@ -1,0 +1,90 @@
+//! Drop-in replacement for ark-blst's `src/gpu.rs` (reference src/gpu.rs:1-286).
+//!
+//! The reference file wraps ec-gpu-gen's generated kernel: per call it enumerates devices, builds a
+//! `Program`, uploads bases and exponents, launches one kernel, downloads 18 944 partials and folds
+//! them on the host (src/gpu.rs:126-241).  This file shrinks to an `extern "C"` block over
+//! `libb200msm.so` (include/b200msm.h); planning, kernels and the whole reduction live there.
+//!
+//! NOT COMPILED IN THIS REPOSITORY: the build image has no cargo/rustc.  The struct sizes the
+//! pointer casts rely on are asserted at compile time below and mirrored by C `_Static_assert`s in
+//! tests/test_layout_mirror.c.
+#![cfg(feature = "b200")]
+
+use ark_ec::AffineRepr;
+
+use crate::{g1::G1Affine, g1::G1Projective, g2::G2Affine, g2::G2Projective, scalar::Scalar};
+
+#[allow(non_camel_case_types)]
+type c_int = core::ffi::c_int;
+
+#[link(name = "b200msm")]
+extern "C" {
+    fn b200msm_g1(bases: *const u64, scalars: *const u64, n: usize, scalars_are_montgomery: c_int, out: *mut u64) -> c_int;
+    fn b200msm_g2(bases: *const u64, scalars: *const u64, n: usize, scalars_are_montgomery: c_int, out: *mut u64) -> c_int;
+}
+
+// The casts below are sound only because every wrapper is #[repr(transparent)] over the blst type
+// (src/g1.rs:54-56,435-437; src/g2.rs:66-68,415-417; src/scalar.rs:23-25).
+const _: () = assert!(core::mem::size_of::<G1Affine>() == 96);
+const _: () = assert!(core::mem::size_of::<G1Projective>() == 144);
+const _: () = assert!(core::mem::size_of::<G2Affine>() == 192);
+const _: () = assert!(core::mem::size_of::<G2Projective>() == 288);
+const _: () = assert!(core::mem::size_of::<Scalar>() == 32);
+const _: () = assert!(core::mem::size_of::<ark_ff::BigInt<4>>() == 32);
+
+/// Scalars as the caller holds them.
+pub(crate) enum Scalars<'a> {
+    /// `&[Scalar]`: Montgomery Fr, passed through untouched (no `into_bigint` pass,
+    /// cf. reference src/g1.rs:624-627 + src/scalar.rs:450-463 which allocate per element).
+    Montgomery(&'a [Scalar]),
+    /// `&[BigInt<4>]`: canonical little-endian limbs (`msm_bigint`).
+    BigInt(&'a [ark_ff::BigInt<4>]),
+}
+
+impl Scalars<'_> {
+    fn len(&self) -> usize {
+        match self {
+            Scalars::Montgomery(s) => s.len(),
+            Scalars::BigInt(s) => s.len(),
+        }
+    }
+    fn ptr_and_flag(&self) -> (*const u64, c_int) {
+        match self {
+            Scalars::Montgomery(s) => (s.as_ptr() as *const u64, 1),
+            Scalars::BigInt(s) => (s.as_ptr() as *const u64, 0),
+        }
+    }
+}
+
+/// `Err(min(len))` on a length mismatch (arkworks' convention for `msm`), `Err(0)` on any device
+/// error (the reference GPU arm's convention, src/g1.rs:628-630). Never panics, never unwinds
+/// across the FFI boundary (the reference `assert_eq!`s and `expect`s, src/gpu.rs:131,235-237).
+pub(crate) fn msm_g1(bases: &[G1Affine], scalars: Scalars<'_>) -> Result<G1Projective, usize> {
+    if bases.len() != scalars.len() {
+        return Err(bases.len().min(scalars.len()));
+    }
+    let (sp, mont) = scalars.ptr_and_flag();
+    let mut out = core::mem::MaybeUninit::<G1Projective>::uninit();
+    let rc = unsafe { b200msm_g1(bases.as_ptr() as *const u64, sp, bases.len(), mont, out.as_mut_ptr() as *mut u64) };
+    if rc != 0 {
+        return Err(0);
+    }
+    Ok(unsafe { out.assume_init() })
+}
+
+pub(crate) fn msm_g2(bases: &[G2Affine], scalars: Scalars<'_>) -> Result<G2Projective, usize> {
+    if bases.len() != scalars.len() {
+        return Err(bases.len().min(scalars.len()));
+    }
+    let (sp, mont) = scalars.ptr_and_flag();
+    let mut out = core::mem::MaybeUninit::<G2Projective>::uninit();
+    let rc = unsafe { b200msm_g2(bases.as_ptr() as *const u64, sp, bases.len(), mont, out.as_mut_ptr() as *mut u64) };
+    if rc != 0 {
+        return Err(0);
+    }
+    Ok(unsafe { out.assume_init() })
+}
+
+// keep the generic bound the old entry point had so call sites outside g1.rs/g2.rs still name it
+#[allow(dead_code)]
+pub(crate) fn _assert_affine<G: AffineRepr>() {}

@@ -81,3 +81,14 @@ def test_product_does_not_touch_the_oracle():
                         if re.search(r"(import|include|dlopen|CDLL).*(oracle|msm_ref)", line):
                             bad.append((f, line.strip()))
     assert not bad, bad
+
+
+def test_layout_mirror_compiles():
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "test_layout_mirror.c")], check=True)
+
+
+def test_cpp_mirror_compiles():
+    """the C++ host mirror of VariableBaseMSM is header-only and must compile stand-alone"""
+    src = '#include "ark_blst_b200/host/ark_blst_msm.hpp"\nint main(){ return ark_blst::G1Projective::NEGATION_IS_CHEAP ? 0 : 1; }\n'
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", ROOT, "-x", "c++", "-"], input=src, text=True, check=True)
