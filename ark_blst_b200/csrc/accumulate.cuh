@@ -38,14 +38,21 @@ k_accumulate(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ va
     if (e - s > heavy_thr) return;  // written by k_heavy_final
     xyzz<F> acc;
     xyzz_set_inf(acc);
+    uint32_t v = s < e ? vals[s] : 0;
     for (uint32_t j = s; j < e; j++) {
-        uint32_t v = vals[j];
         const uint32_t *p = bases + (size_t)(v & 0x7fffffffu) * (2 * W);
+        const uint32_t sign = v >> 31;
         F x, y;
         f_load(x, p);
         f_load(y, p + W);
+        if (j + 1 < e) {  // pull the next point towards L1 while this one is being added
+            v = vals[j + 1];
+            const char *q = reinterpret_cast<const char *>(bases + (size_t)(v & 0x7fffffffu) * (2 * W));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(q + 8 * W - 4));
+        }
         if (f_is_zero(x) && f_is_zero(y)) continue;  // identity base
-        f_cneg(y, y, v >> 31);
+        f_cneg(y, y, sign);
         xyzz_madd(acc, x, y);
     }
     xyzz_store(buckets + (size_t)b * (4 * W), acc);

@@ -87,9 +87,10 @@ int auto_window(size_t n, bool g2) {
 struct DeviceCtx {
     int dev = -1;
     std::mutex mu;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_scalars = nullptr, ev_bases = nullptr;
     DevBuf bases, scalars, keys[2], vals[2], cubtmp, start, cnt[2], ord[2], buckets, lvlR[2], lvlC[2], out;
-    DevBuf hvy_hdr, hvy_buckets, hvy_tasks, hvy_partials;
+    DevBuf hvy_hdr, hvy_buckets, hvy_tasks, hvy_partials, treeS[2], treeV[2], treeC[2], wsum;
     cudaEvent_t ev[8] = {};
     double phase_ms[8] = {};
     bool phase_pending = false;
@@ -97,7 +98,7 @@ struct DeviceCtx {
     void release_all() {
         for (DevBuf *b : {&bases, &scalars, &keys[0], &keys[1], &vals[0], &vals[1], &cubtmp, &start, &cnt[0], &cnt[1],
                           &ord[0], &ord[1], &buckets, &lvlR[0], &lvlR[1], &lvlC[0], &lvlC[1], &out, &hvy_hdr, &hvy_buckets,
-                          &hvy_tasks, &hvy_partials})
+                          &hvy_tasks, &hvy_partials, &treeS[0], &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum})
             b->release();
     }
 };
@@ -134,6 +135,9 @@ int engine_init_locked(int first, int ndev) {
         c->sm_count = p.multiProcessorCount;
         CUDA_TRY(cudaSetDevice(d));
         CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_scalars, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_bases, cudaEventDisableTiming));
         for (auto &ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
         g_eng.ctx.push_back(std::move(c));
     }
@@ -154,8 +158,10 @@ DeviceCtx *ctx_for_current_device() {
 
 // The pipeline on one device. Inputs already in device memory; d_out receives 3 field elements.
 // Must be called with ctx.mu held and ctx.dev current. Asynchronous on `st`.
+// `bases_ready` (optional): an event after which d_bases is valid — the scalar-side phases
+// (digits, sort, bucket offsets) do not read the bases, so they overlap the bases' H2D copy.
 int run_group(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scalars_v, size_t n, int mont, void *d_out_v,
-              cudaStream_t st) {
+              cudaStream_t st, cudaEvent_t bases_ready = nullptr) {
     if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "group must be B200MSM_G1 or B200MSM_G2");
     const bool g2 = group == B200MSM_G2;
     const uint32_t *d_bases = (const uint32_t *)d_bases_v, *d_scalars = (const uint32_t *)d_scalars_v;
@@ -185,16 +191,20 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_sca
         if (int rc = cx.vals[i].reserve(m * 4)) return rc;
         if (int rc = cx.cnt[i].reserve((size_t)pl.nb * 4)) return rc;
         if (int rc = cx.ord[i].reserve((size_t)pl.nb * 4)) return rc;
-        size_t lvl = (size_t)pl.nwin * std::max<size_t>(1, pl.nbw / 8) * PB;
+        size_t lvl = (size_t)pl.nwin * std::max<size_t>(1, pl.nbw / 32) * PB;
         if (int rc = cx.lvlR[i].reserve(lvl)) return rc;
         if (int rc = cx.lvlC[i].reserve(lvl)) return rc;
     }
     if (int rc = cx.start.reserve(((size_t)pl.nb + 2) * 4)) return rc;
     if (int rc = cx.buckets.reserve((size_t)pl.nb * PB)) return rc;
-    // heavy buckets: more than 3× the mean occupancy of a window's buckets (never reached by a
-    // uniform distribution); worst-case list sizes follow from Σ counts = m
+    // heavy buckets: one thread per bucket is the efficient shape (≈0.31 product-times per entry
+    // per warp vs ≈1 for the block-cooperative path), so a bucket only counts as heavy when its
+    // serial chain would be a visible fraction (≈8 %) of the whole accumulation — the kernel lasts
+    // ≈ m/175k bucket-entry times — or when it exceeds 3× the mean occupancy, whichever is larger.
+    // Buckets are taken in decreasing-size order, so the long chains start first.
+    // Worst-case list sizes follow from Σ counts = m.
     const uint32_t avg = (uint32_t)((n + pl.nbw - 1) / pl.nbw);
-    const uint32_t heavy_thr = std::max<uint32_t>(32, 3 * avg);
+    const uint32_t heavy_thr = std::max<uint32_t>(std::max<uint32_t>(32, 3 * avg), (uint32_t)(m / 175000));
     const size_t max_heavy = m / (heavy_thr + 1) + 1, max_tasks = m / HEAVY_CHUNK + max_heavy + 1;
     if (int rc = cx.hvy_hdr.reserve(16)) return rc;
     if (int rc = cx.hvy_buckets.reserve(max_heavy * 12)) return rc;
@@ -227,32 +237,54 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_sca
     mark();
     // 4. bucket accumulation
     CUDA_TRY(cudaMemsetAsync(cx.hvy_hdr.p, 0, 16, st));
+    if (bases_ready) CUDA_TRY(cudaStreamWaitEvent(st, bases_ready, 0));
     (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals[sel], start, ord[osel], pl.nb, heavy_thr,
                                                        cx.buckets.as<uint32_t>(), st);
     (g2 ? launch_heavy_g2 : launch_heavy_g1)(d_bases, vals[sel], start, ord[osel], pl.nb, heavy_thr, cx.hvy_hdr.p,
                                              cx.hvy_buckets.p, cx.hvy_tasks.p, cx.hvy_partials.as<uint32_t>(),
                                              cx.buckets.as<uint32_t>(), cx.sm_count * 4, st);
     mark();
-    // 5. per-window weighted bucket sums, by levels
+    // 5. per-window weighted bucket sums: running-sum levels of fan-in 32 while the arrays are long
+    //    (throughput-bound), then a log-depth tree (latency-bound part)
     const uint32_t *X = cx.buckets.as<uint32_t>();
     const uint32_t *Cin = nullptr;
     uint32_t len = pl.nbw;
     int log2M = 0, pp = 0;
-    while (len > 1) {
-        uint32_t seg = len >= 4096 ? 32 : (len >= 64 ? 8 : len);
-        (g2 ? launch_wsum_level_g2 : launch_wsum_level_g1)(X, Cin, len, seg, log2M, (uint32_t)pl.nwin,
+    while (len > 2048) {
+        (g2 ? launch_wsum_level_g2 : launch_wsum_level_g1)(X, Cin, len, 32, log2M, (uint32_t)pl.nwin,
                                                            cx.lvlR[pp].as<uint32_t>(), cx.lvlC[pp].as<uint32_t>(), st);
         X = cx.lvlR[pp].as<uint32_t>();
         Cin = cx.lvlC[pp].as<uint32_t>();
-        int l2 = 0;
-        while ((1u << l2) < seg) l2++;
-        log2M += l2;
-        len /= seg;
+        log2M += 5;
+        len /= 32;
         pp ^= 1;
     }
+    const uint32_t S = len;
+    int logS = 0;
+    while ((1u << logS) < S) logS++;
+    const size_t tstride = std::max<uint32_t>(1, S / 2);  // points per window in every tree array
+    for (int i = 0; i < 2; i++) {
+        if (int rc = cx.treeS[i].reserve((size_t)pl.nwin * tstride * PB)) return rc;
+        if (int rc = cx.treeV[i].reserve((size_t)pl.nwin * tstride * PB)) return rc;
+        if (int rc = cx.treeC[i].reserve((size_t)pl.nwin * tstride * PB)) return rc;
+    }
+    if (int rc = cx.wsum.reserve((size_t)pl.nwin * PB)) return rc;
+    const uint32_t *Sin = X, *Ccur = Cin;
+    size_t sin_stride = S, cin_stride = S;
+    int cur = 0;
+    for (int j = 0; j < logS; j++) {
+        (g2 ? launch_tree_level_g2 : launch_tree_level_g1)(Sin, sin_stride, cx.treeV[cur].as<uint32_t>(), Ccur, cin_stride,
+                                                           cx.treeS[cur ^ 1].as<uint32_t>(), cx.treeV[cur ^ 1].as<uint32_t>(),
+                                                           cx.treeC[cur ^ 1].as<uint32_t>(), tstride, S, j, (uint32_t)pl.nwin, st);
+        cur ^= 1;
+        Sin = cx.treeS[cur].as<uint32_t>();
+        sin_stride = tstride;
+        if (Cin) { Ccur = cx.treeC[cur].as<uint32_t>(); cin_stride = tstride; }
+    }
     mark();
-    // 6. windows → one Jacobian point
-    (g2 ? launch_combine_g2 : launch_combine_g1)(Cin, X, pl.nwin, pl.c, d_out, st);
+    // 6. window values and Horner over the windows → one Jacobian point
+    (g2 ? launch_combine_g2 : launch_combine_g1)(Sin, cx.treeV[cur].as<uint32_t>(), Cin ? Ccur : nullptr, tstride, logS, log2M,
+                                                 pl.nwin, pl.c, cx.wsum.as<uint32_t>(), d_out, st);
     mark();
     CUDA_TRY(cudaGetLastError());
     cx.phase_pending = prof;  // elapsed times are read lazily by b200msm_last_phase_ms (no sync here)
@@ -315,15 +347,22 @@ int msm_host(int group, const uint64_t *bases, const uint64_t *scalars, size_t n
             continue;
         }
         if ((rc = cx.scalars.reserve(cnt[d] * 32))) break;
-        cudaMemcpyAsync(cx.scalars.p, scalars + 4 * lo[d], cnt[d] * 32, cudaMemcpyHostToDevice, cx.stream);
+        // scalars first (the digit kernel needs them), then the bases behind them on the same copy
+        // stream; the compute stream only waits for the bases right before the accumulation
+        cudaMemcpyAsync(cx.scalars.p, scalars + 4 * lo[d], cnt[d] * 32, cudaMemcpyHostToDevice, cx.copy_stream);
+        cudaEventRecord(cx.ev_scalars, cx.copy_stream);
+        cudaStreamWaitEvent(cx.stream, cx.ev_scalars, 0);
         const void *db;
+        cudaEvent_t ready = nullptr;
         if (resident) db = resident->shard[d].p;
         else {
             if ((rc = cx.bases.reserve(cnt[d] * AB))) break;
-            cudaMemcpyAsync(cx.bases.p, (const char *)bases + lo[d] * AB, cnt[d] * AB, cudaMemcpyHostToDevice, cx.stream);
+            cudaMemcpyAsync(cx.bases.p, (const char *)bases + lo[d] * AB, cnt[d] * AB, cudaMemcpyHostToDevice, cx.copy_stream);
+            cudaEventRecord(cx.ev_bases, cx.copy_stream);
             db = cx.bases.p;
+            ready = cx.ev_bases;
         }
-        rc = run_group(group, cx, db, cx.scalars.p, cnt[d], mont, cx.out.p, cx.stream);
+        rc = run_group(group, cx, db, cx.scalars.p, cnt[d], mont, cx.out.p, cx.stream, ready);
     }
     if (!rc) {
         DeviceCtx &c0 = *g_eng.ctx[0];
@@ -373,6 +412,9 @@ void b200msm_shutdown(void) {
         c->release_all();
         for (auto &ev : c->ev) cudaEventDestroy(ev);
         cudaStreamDestroy(c->stream);
+        cudaStreamDestroy(c->copy_stream);
+        cudaEventDestroy(c->ev_scalars);
+        cudaEventDestroy(c->ev_bases);
     }
     g_eng.ctx.clear();
     g_eng.inited = false;

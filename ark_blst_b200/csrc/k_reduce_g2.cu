@@ -9,9 +9,18 @@ void launch_wsum_level_g2(const uint32_t *X, const uint32_t *Cin, uint32_t len, 
     uint32_t nseg = len / m;
     k_wsum_level<fp2><<<blocks_for((size_t)nseg * nwin * 4, 128), 128, 0, st>>>(X, Cin, len, m, log2M, nwin, Rout, Cout);
 }
-void launch_combine_g2(const uint32_t *C, const uint32_t *R, int nwin, int c, uint32_t *out, cudaStream_t st) {
+void launch_tree_level_g2(const uint32_t *Sin, size_t sin_stride, const uint32_t *Vin, const uint32_t *Cin, size_t cin_stride,
+                          uint32_t *Sout, uint32_t *Vout, uint32_t *Cout, size_t out_stride, uint32_t S, int j, uint32_t nwin,
+                          cudaStream_t st) {
     count_launch();
-    k_combine<fp2><<<1, 32, 0, st>>>(C, R, nwin, c, out);
+    size_t quads = (size_t)(S >> (j + 1)) * (j + 1 + (Cin ? 1 : 0)) * nwin;
+    k_tree_level<fp2><<<blocks_for(quads * 4, 128), 128, 0, st>>>(Sin, sin_stride, Vin, Cin, cin_stride, Sout, Vout, Cout,
+                                                                 out_stride, S, j, nwin);
+}
+void launch_combine_g2(const uint32_t *Sroot, const uint32_t *V, const uint32_t *Croot, size_t stride, int logS, int log2M,
+                       int nwin, int c, uint32_t *wsum, uint32_t *out, cudaStream_t st) {
+    count_launch();
+    k_combine<fp2><<<1, 128, 0, st>>>(Sroot, V, Croot, stride, logS, log2M, nwin, c, wsum, out);
 }
 void launch_sum_partials_g2(const uint32_t *partials, int count, uint32_t *out, cudaStream_t st) {
     count_launch();

@@ -38,8 +38,17 @@ void launch_wsum_level_g1(const uint32_t *X, const uint32_t *Cin, uint32_t len, 
                           uint32_t *Rout, uint32_t *Cout, cudaStream_t st);
 void launch_wsum_level_g2(const uint32_t *X, const uint32_t *Cin, uint32_t len, uint32_t m, int log2M, uint32_t nwin,
                           uint32_t *Rout, uint32_t *Cout, cudaStream_t st);
-void launch_combine_g1(const uint32_t *C, const uint32_t *R, int nwin, int c, uint32_t *out, cudaStream_t st);
-void launch_combine_g2(const uint32_t *C, const uint32_t *R, int nwin, int c, uint32_t *out, cudaStream_t st);
+// one level of the log-depth tree over the per-window arrays (see reduce.cuh)
+void launch_tree_level_g1(const uint32_t *Sin, size_t sin_stride, const uint32_t *Vin, const uint32_t *Cin, size_t cin_stride,
+                          uint32_t *Sout, uint32_t *Vout, uint32_t *Cout, size_t out_stride, uint32_t S, int j, uint32_t nwin,
+                          cudaStream_t st);
+void launch_tree_level_g2(const uint32_t *Sin, size_t sin_stride, const uint32_t *Vin, const uint32_t *Cin, size_t cin_stride,
+                          uint32_t *Sout, uint32_t *Vout, uint32_t *Cout, size_t out_stride, uint32_t S, int j, uint32_t nwin,
+                          cudaStream_t st);
+void launch_combine_g1(const uint32_t *Sroot, const uint32_t *V, const uint32_t *Croot, size_t stride, int logS, int log2M,
+                       int nwin, int c, uint32_t *wsum, uint32_t *out, cudaStream_t st);
+void launch_combine_g2(const uint32_t *Sroot, const uint32_t *V, const uint32_t *Croot, size_t stride, int logS, int log2M,
+                       int nwin, int c, uint32_t *wsum, uint32_t *out, cudaStream_t st);
 void launch_sum_partials_g1(const uint32_t *partials, int count, uint32_t *out, cudaStream_t st);
 void launch_sum_partials_g2(const uint32_t *partials, int count, uint32_t *out, cudaStream_t st);
 

@@ -28,8 +28,11 @@ k_wsum_level(const uint32_t *__restrict__ X, const uint32_t *__restrict__ Cin, u
     xyzz<F> run, acc, tmp;
     xyzz_set_inf(run);
     xyzz_set_inf(acc);
+    xyzz<F> nxt;
+    xyzz_load(nxt, x + (size_t)(m - 1) * PW);
     for (uint32_t j = m; j-- > 0;) {
-        xyzz_load(tmp, x + (size_t)j * PW);
+        tmp = nxt;
+        if (j) xyzz_load(nxt, x + (size_t)(j - 1) * PW);  // prefetch: the global load leaves the chain
         xyzz_add_quad(run, tmp);
         if (j) xyzz_add_quad(acc, run);            // warp-uniform: element 0 has weight 0
     }
@@ -37,28 +40,99 @@ k_wsum_level(const uint32_t *__restrict__ X, const uint32_t *__restrict__ Cin, u
     for (int k = 0; k < log2M; k++) xyzz_dbl_quad(acc);
     if (Cin) {
         const uint32_t *ci = Cin + ((size_t)w * len + (size_t)s * m) * PW;
+        xyzz_load(nxt, ci);
         for (uint32_t j = 0; j < m; j++) {
-            xyzz_load(tmp, ci + (size_t)j * PW);
+            tmp = nxt;
+            if (j + 1 < m) xyzz_load(nxt, ci + (size_t)(j + 1) * PW);
             xyzz_add_quad(acc, tmp);
         }
     }
     if (writer) xyzz_store(Cout + ((size_t)w * nseg + s) * PW, acc);
 }
 
-// window value_w = C[w] + R[w]; result = Σ_w 2^(c·w)·value_w by Horner from the top window,
-// written as a Jacobian point (blst_p1 / blst_p2 layout). One quad.
+// ---- upper part of the reduction: a log-depth tree instead of more running-sum levels --------
+// For X[0..S) per window, Wsum0(X) = Σ_k 2^k·V_k with V_k = Σ_{i: bit k of i set} X_i.  A node
+// covering 2^j consecutive elements keeps its sum and its j partial V's; merging two siblings is
+//     S' = S_l + S_r,   V'_k = V_l,k + V_r,k (k < j),   V'_j = S_r,   C' = C_l + C_r
+// — independent additions, one kernel launch per tree level, every addition on its own quad.
+// Depth log2(S) additions instead of ~3·m per running-sum level.
+// Task layout at level j: per = j + 1 (+1 with a carried C array) additions per merged node.
 template <class F>
-__global__ void k_combine(const uint32_t *__restrict__ C, const uint32_t *__restrict__ R, int nwin, int c,
-                          uint32_t *__restrict__ out) {
+__global__ void __launch_bounds__(128)
+k_tree_level(const uint32_t *__restrict__ Sin, size_t sin_stride, const uint32_t *__restrict__ Vin,
+             const uint32_t *__restrict__ Cin, size_t cin_stride, uint32_t *__restrict__ Sout, uint32_t *__restrict__ Vout,
+             uint32_t *__restrict__ Cout, size_t out_stride, uint32_t S, int j, uint32_t nwin) {
     constexpr int PW = 4 * field_words<F>::value;
-    if (blockIdx.x) return;                        // one warp; quad 0 writes
+    const uint32_t n2 = S >> (j + 1);              // merged nodes per window
+    const uint32_t per = (uint32_t)j + 1 + (Cin ? 1 : 0);
+    const uint32_t ntask = n2 * per * nwin;
+    uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const bool live = idx < ntask;
+    if (!live) idx = 0;                            // idle quads tag along so the warp stays whole
+    const bool writer = live && (threadIdx.x & 3) == 0;
+    const uint32_t w = idx / (n2 * per), rem = idx % (n2 * per);
+    const uint32_t t = rem / per, r = rem % per;
+    const uint32_t *pa, *pb;
+    uint32_t *pd;
+    if (r < (uint32_t)j) {                         // V_k of the two children (packed, stride j per node)
+        const uint32_t *v = Vin + (size_t)w * out_stride * PW;
+        pa = v + ((size_t)(2 * t) * j + r) * PW;
+        pb = v + ((size_t)(2 * t + 1) * j + r) * PW;
+        pd = Vout + ((size_t)w * out_stride + (size_t)t * (j + 1) + r) * PW;
+    } else if (r == (uint32_t)j) {                 // node sums
+        const uint32_t *sp = Sin + (size_t)w * sin_stride * PW;
+        pa = sp + (size_t)(2 * t) * PW;
+        pb = sp + (size_t)(2 * t + 1) * PW;
+        pd = Sout + ((size_t)w * out_stride + t) * PW;
+    } else {                                       // carried C sums
+        const uint32_t *cp = Cin + (size_t)w * cin_stride * PW;
+        pa = cp + (size_t)(2 * t) * PW;
+        pb = cp + (size_t)(2 * t + 1) * PW;
+        pd = Cout + ((size_t)w * out_stride + t) * PW;
+    }
+    xyzz<F> a, b;
+    xyzz_load(a, pa);
+    xyzz_load(b, pb);
+    if (writer && r == (uint32_t)j)                // V'_j = S_r
+        xyzz_store(Vout + ((size_t)w * out_stride + (size_t)t * (j + 1) + j) * PW, b);
+    xyzz_add_quad(a, b);
+    if (writer) xyzz_store(pd, a);
+}
+
+// Per window: value_w = C_root + 2^log2M·(Σ_k 2^k V_k) + S_root (one quad per window, Horner over
+// k), then result = Σ_w 2^(c·w)·value_w by Horner from the top window (warp 0), written as a
+// Jacobian point (blst_p1 / blst_p2 layout). One block of 128 threads = 32 quads.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_combine(const uint32_t *__restrict__ Sroot, const uint32_t *__restrict__ V, const uint32_t *__restrict__ Croot,
+          size_t stride, int logS, int log2M, int nwin, int c, uint32_t *__restrict__ wsum, uint32_t *__restrict__ out) {
+    constexpr int PW = 4 * field_words<F>::value;
+    const int qd = threadIdx.x >> 2;
     xyzz<F> acc, a;
-    xyzz_set_inf(acc);
-    for (int w = nwin - 1; w >= 0; w--) {
-        for (int k = 0; k < c; k++) xyzz_dbl_quad(acc);
-        xyzz_load(a, C + (size_t)w * PW);
+    for (int base = 0; base < nwin; base += 32) {  // block-uniform trip count
+        const int w = base + qd < nwin ? base + qd : 0;  // surplus quads recompute window 0
+        xyzz_set_inf(acc);
+        const uint32_t *v = V + (size_t)w * stride * PW;
+        for (int k = logS - 1; k >= 0; k--) {      // T = Σ_k 2^k V_k
+            xyzz_dbl_quad(acc);
+            xyzz_load(a, v + (size_t)k * PW);
+            xyzz_add_quad(acc, a);
+        }
+        for (int k = 0; k < log2M; k++) xyzz_dbl_quad(acc);
+        if (Croot) {
+            xyzz_load(a, Croot + (size_t)w * stride * PW);
+            xyzz_add_quad(acc, a);
+        }
+        xyzz_load(a, Sroot + (size_t)w * stride * PW);
         xyzz_add_quad(acc, a);
-        xyzz_load(a, R + (size_t)w * PW);
+        if (base + qd < nwin && (threadIdx.x & 3) == 0) xyzz_store(wsum + (size_t)(base + qd) * PW, acc);
+    }
+    __syncthreads();                               // window sums visible to warp 0
+    if (threadIdx.x >= 32) return;                 // warp 0 finishes (its 8 quads in lock-step)
+    xyzz_set_inf(acc);
+    for (int ww = nwin - 1; ww >= 0; ww--) {
+        for (int k = 0; k < c; k++) xyzz_dbl_quad(acc);
+        xyzz_load(a, wsum + (size_t)ww * PW);
         xyzz_add_quad(acc, a);
     }
     if (threadIdx.x == 0) {

@@ -316,7 +316,8 @@ def run_ours(args):
                    "what": "oracle/libmsm_ref.so: C restatement of blst 0.3.10 Pippenger (portable u128 Montgomery, "
                            "no hand-written asm); real blst cannot be built here (Rust, no cargo)"}
 
-        c, W, fpmul_total, fpmul_acc = work_model(n, g2)
+        c, W, _, fpmul_acc = work_model(n, g2)            # what each GPU's accumulate kernel runs
+        _, _, fpmul_total, _ = work_model(n_total, g2)     # single-problem numerator
         ph = {k: sum(p[k] for p in phases) / len(phases) for k in phases[0] if k != "valid"}
         acc_s = ph["accumulate"] * 1e-3
         imad_peak = peak["imad_per_s"]
