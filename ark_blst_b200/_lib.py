@@ -30,8 +30,11 @@ SIGNATURES = {
     "b200msm_run": (ctypes.c_int, [vp, u64p, ctypes.c_size_t, ctypes.c_int, u64p]),
     "b200msm_run_device": (ctypes.c_int, [ctypes.c_int, vp, vp, ctypes.c_size_t, ctypes.c_int, vp, vp]),
     "b200msm_sum_partials_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int, vp, vp]),
+    "b200msm_normalize_batch": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_size_t, u64p]),
+    "b200msm_normalize_batch_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, vp, vp]),
     "b200msm_launch_count": (ctypes.c_ulonglong, []),
     "b200msm_set_window_bits": (ctypes.c_int, [ctypes.c_int]),
+    "b200msm_set_max_chunk": (ctypes.c_int, [ctypes.c_size_t]),
     "b200msm_set_profiling": (ctypes.c_int, [ctypes.c_int]),
     "b200msm_last_phase_ms": (ctypes.c_int, [f64p]),
     "b200msm_synth_bases_device": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint64, ctypes.c_size_t, vp, vp]),

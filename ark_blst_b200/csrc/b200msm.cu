@@ -87,18 +87,29 @@ int auto_window(size_t n, bool g2) {
 struct DeviceCtx {
     int dev = -1;
     std::mutex mu;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_scalars = nullptr, ev_bases = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
+    cudaEvent_t ev_scalars = nullptr, ev_bases = nullptr, ev_busy = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    bool busy_valid = false;
     DevBuf bases, scalars, keys[2], vals[2], cubtmp, start, cnt[2], ord[2], buckets, lvlR[2], lvlC[2], out;
-    DevBuf hvy_hdr, hvy_buckets, hvy_tasks, hvy_partials, treeS[2], treeV[2], treeC[2], wsum;
+    DevBuf hvy_hdr, hvy_buckets, hvy_tasks, hvy_partials, treeS[2], treeV[2], treeC[2], wsum, chunk_partials, norm_in, norm_out;
     cudaEvent_t ev[8] = {};
     double phase_ms[8] = {};
     bool phase_pending = false;
     int sm_count = 0;
+    std::vector<DevBuf *> scratch() {
+        return {&keys[0], &keys[1], &vals[0], &vals[1], &cubtmp, &start, &cnt[0], &cnt[1], &ord[0], &ord[1], &buckets,
+                &lvlR[0], &lvlR[1], &lvlC[0], &lvlC[1], &hvy_hdr, &hvy_buckets, &hvy_tasks, &hvy_partials, &treeS[0],
+                &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum};
+    }
+    size_t scratch_bytes() {
+        size_t s = 0;
+        for (DevBuf *b : scratch()) s += b->cap;
+        return s;
+    }
     void release_all() {
         for (DevBuf *b : {&bases, &scalars, &keys[0], &keys[1], &vals[0], &vals[1], &cubtmp, &start, &cnt[0], &cnt[1],
                           &ord[0], &ord[1], &buckets, &lvlR[0], &lvlR[1], &lvlC[0], &lvlC[1], &out, &hvy_hdr, &hvy_buckets,
-                          &hvy_tasks, &hvy_partials, &treeS[0], &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum})
+                          &hvy_tasks, &hvy_partials, &treeS[0], &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum, &chunk_partials, &norm_in, &norm_out})
             b->release();
     }
 };
@@ -108,6 +119,7 @@ struct Engine {
     bool inited = false;
     std::vector<std::unique_ptr<DeviceCtx>> ctx;
     int window_override = 0;
+    size_t max_chunk_override = 0;  // tests: force chunked execution at small n
     bool profiling = false;
 };
 Engine g_eng;
@@ -138,6 +150,10 @@ int engine_init_locked(int first, int ndev) {
         CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_scalars, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_bases, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_busy, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
         for (auto &ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
         g_eng.ctx.push_back(std::move(c));
     }
@@ -160,7 +176,7 @@ DeviceCtx *ctx_for_current_device() {
 // Must be called with ctx.mu held and ctx.dev current. Asynchronous on `st`.
 // `bases_ready` (optional): an event after which d_bases is valid — the scalar-side phases
 // (digits, sort, bucket offsets) do not read the bases, so they overlap the bases' H2D copy.
-int run_group(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scalars_v, size_t n, int mont, void *d_out_v,
+int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scalars_v, size_t n, int mont, void *d_out_v,
               cudaStream_t st, cudaEvent_t bases_ready = nullptr) {
     if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "group must be B200MSM_G1 or B200MSM_G2");
     const bool g2 = group == B200MSM_G2;
@@ -172,7 +188,6 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_sca
         CUDA_TRY(cudaMemsetAsync(d_out, 0, 3 * W * 4, st));
         return 0;
     }
-    if (n >= (1ull << 31)) return fail(B200MSM_EINVAL, "n must be < 2^31 per device");
     Plan pl;
     pl.c = g_eng.window_override > 0 ? g_eng.window_override : auto_window(n, g2);
     pl.c = std::max(2, std::min(pl.c, 24));
@@ -238,11 +253,17 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_sca
     // 4. bucket accumulation
     CUDA_TRY(cudaMemsetAsync(cx.hvy_hdr.p, 0, 16, st));
     if (bases_ready) CUDA_TRY(cudaStreamWaitEvent(st, bases_ready, 0));
-    (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals[sel], start, ord[osel], pl.nb, heavy_thr,
-                                                       cx.buckets.as<uint32_t>(), st);
+    // heavy buckets run on a side stream next to the light kernel (disjoint outputs): each fills
+    // the SMs the other leaves idle at its tail
+    CUDA_TRY(cudaEventRecord(cx.ev_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(cx.aux_stream, cx.ev_fork, 0));
     (g2 ? launch_heavy_g2 : launch_heavy_g1)(d_bases, vals[sel], start, ord[osel], pl.nb, heavy_thr, cx.hvy_hdr.p,
                                              cx.hvy_buckets.p, cx.hvy_tasks.p, cx.hvy_partials.as<uint32_t>(),
-                                             cx.buckets.as<uint32_t>(), cx.sm_count * 4, st);
+                                             cx.buckets.as<uint32_t>(), cx.sm_count * 4, cx.aux_stream);
+    CUDA_TRY(cudaEventRecord(cx.ev_join, cx.aux_stream));
+    (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals[sel], start, ord[osel], pl.nb, heavy_thr,
+                                                       cx.buckets.as<uint32_t>(), st);
+    CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_join, 0));
     mark();
     // 5. per-window weighted bucket sums: running-sum levels of fan-in 32 while the arrays are long
     //    (throughput-bound), then a log-depth tree (latency-bound part)
@@ -289,6 +310,60 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_sca
     CUDA_TRY(cudaGetLastError());
     cx.phase_pending = prof;  // elapsed times are read lazily by b200msm_last_phase_ms (no sync here)
     return 0;
+}
+
+// Scratch bytes one pass over n points needs (sort double buffers dominate).
+size_t pass_scratch_bytes(size_t n, bool g2, int c_override) {
+    int c = c_override > 0 ? c_override : auto_window(n, g2);
+    c = std::max(2, std::min(c, 24));
+    size_t nwin = (256 + c - 1) / c, nb = nwin << (c - 1), m = n * nwin;
+    size_t PB = g2 ? 384 : 192;
+    return m * 16 + nb * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + (64u << 20);
+}
+
+// The whole MSM on one device: one pass when it fits, otherwise the chunking the reference left
+// as a TODO (src/gpu.rs:238-239; its calc_chunk_size result is never used, :64-85,114): the points
+// are cut into equal chunks whose sort arrays stay below 2^32 entries and within the free HBM,
+// each chunk yields a Jacobian partial, and the partials are added on the device.
+int run_group(int group, DeviceCtx &cx, const void *d_bases, const void *d_scalars, size_t n, int mont, void *d_out,
+              cudaStream_t st, cudaEvent_t bases_ready = nullptr) {
+    if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "group must be B200MSM_G1 or B200MSM_G2");
+    const bool g2 = group == B200MSM_G2;
+    // GPU-side serialisation of the context's scratch arena across streams
+    if (cx.busy_valid) CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_busy, 0));
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = (size_t)((double)(free_b + cx.scratch_bytes()) * 0.85);
+    if (g_eng.max_chunk_override) budget = 0;  // tests: force chunking by point count only
+    size_t chunks = 1;
+    auto too_big = [&](size_t cn) {
+        if (g_eng.max_chunk_override) return cn > g_eng.max_chunk_override;
+        int c = g_eng.window_override > 0 ? g_eng.window_override : auto_window(cn, g2);
+        size_t nwin = (256 + c - 1) / c;
+        return cn * nwin >= 0xfff00000ull || cn >= (1ull << 31) || pass_scratch_bytes(cn, g2, g_eng.window_override) > budget;
+    };
+    while (too_big((n + chunks - 1) / chunks)) {
+        chunks *= 2;
+        if (chunks > (1u << 20)) return fail(B200MSM_ENOMEM, "cannot fit even a tiny chunk of this MSM in device memory");
+    }
+    int rc = 0;
+    if (chunks == 1) {
+        rc = run_pass(group, cx, d_bases, d_scalars, n, mont, d_out, st, bases_ready);
+    } else {
+        const size_t AB = g2 ? 192 : 96, JB = g2 ? 288 : 144;
+        if ((rc = cx.chunk_partials.reserve(chunks * JB))) return rc;
+        for (size_t k = 0; k < chunks && !rc; k++) {
+            size_t lo = n * k / chunks, hi = n * (k + 1) / chunks;
+            rc = run_pass(group, cx, (const char *)d_bases + lo * AB, (const char *)d_scalars + lo * 32, hi - lo, mont,
+                          (char *)cx.chunk_partials.p + k * JB, st, k == 0 ? bases_ready : nullptr);
+        }
+        if (!rc) (g2 ? launch_sum_partials_g2 : launch_sum_partials_g1)((const uint32_t *)cx.chunk_partials.p, (int)chunks, (uint32_t *)d_out, st);
+    }
+    if (!rc) {
+        CUDA_TRY(cudaEventRecord(cx.ev_busy, st));
+        cx.busy_valid = true;
+    }
+    return rc;
 }
 
 size_t aff_bytes(int group) { return group == B200MSM_G2 ? 192 : 96; }
@@ -415,6 +490,10 @@ void b200msm_shutdown(void) {
         cudaStreamDestroy(c->copy_stream);
         cudaEventDestroy(c->ev_scalars);
         cudaEventDestroy(c->ev_bases);
+        cudaEventDestroy(c->ev_busy);
+        cudaEventDestroy(c->ev_fork);
+        cudaEventDestroy(c->ev_join);
+        cudaStreamDestroy(c->aux_stream);
     }
     g_eng.ctx.clear();
     g_eng.inited = false;
@@ -501,9 +580,47 @@ int b200msm_sum_partials_device(int group, const void *d_partials, int count, vo
 
 unsigned long long b200msm_launch_count(void) { return __atomic_load_n(&g_own_launches, __ATOMIC_RELAXED); }
 
+int b200msm_normalize_batch_device(int group, const void *d_proj, size_t n, void *d_affine, void *stream) {
+    if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "bad group");
+    if (n == 0) return 0;
+    if (!d_proj || !d_affine) return fail(B200MSM_EINVAL, "null pointer");
+    if (int rc = engine_init(-1, 1)) return rc;
+    DeviceCtx *cx = ctx_for_current_device();
+    if (!cx) return fail(B200MSM_EINVAL, "current device is not bound to the engine");
+    launch_normalize_batch(group == B200MSM_G2, (const uint32_t *)d_proj, n, (uint32_t *)d_affine, cx->sm_count, (cudaStream_t)stream);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int b200msm_normalize_batch(int group, const uint64_t *proj, size_t n, uint64_t *affine_out) {
+    if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "bad group");
+    if (n == 0) return 0;
+    if (!proj || !affine_out) return fail(B200MSM_EINVAL, "null pointer");
+    if (int rc = engine_init(-1, 1)) return rc;
+    DeviceCtx &cx = *g_eng.ctx[0];
+    std::lock_guard<std::mutex> lk(cx.mu);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(cx.dev);
+    const size_t JB = jac_bytes(group), AB = aff_bytes(group);
+    int rc = 0;
+    if (!(rc = cx.norm_in.reserve(n * JB)) && !(rc = cx.norm_out.reserve(n * AB))) {
+        cudaMemcpyAsync(cx.norm_in.p, proj, n * JB, cudaMemcpyHostToDevice, cx.stream);
+        launch_normalize_batch(group == B200MSM_G2, cx.norm_in.as<uint32_t>(), n, cx.norm_out.as<uint32_t>(), cx.sm_count, cx.stream);
+        cudaMemcpyAsync(affine_out, cx.norm_out.p, n * AB, cudaMemcpyDeviceToHost, cx.stream);
+        cudaError_t e = cudaStreamSynchronize(cx.stream);
+        if (e != cudaSuccess) rc = fail(B200MSM_ECUDA, std::string("normalize_batch: ") + cudaGetErrorString(e));
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
 int b200msm_set_window_bits(int c) {
     if (c < 0 || c == 1 || c > 24) return fail(B200MSM_EINVAL, "window bits must be 0 (auto) or 2..24");
     g_eng.window_override = c;
+    return 0;
+}
+int b200msm_set_max_chunk(size_t max_points_per_pass) {
+    g_eng.max_chunk_override = max_points_per_pass;
     return 0;
 }
 int b200msm_set_profiling(int on) {

@@ -52,6 +52,9 @@ void launch_combine_g2(const uint32_t *Sroot, const uint32_t *V, const uint32_t 
 void launch_sum_partials_g1(const uint32_t *partials, int count, uint32_t *out, cudaStream_t st);
 void launch_sum_partials_g2(const uint32_t *partials, int count, uint32_t *out, cudaStream_t st);
 
+// k_normalize.cu
+void launch_normalize_batch(int g2, const uint32_t *proj, size_t n, uint32_t *aff, int sm_count, cudaStream_t st);
+
 // k_synth_g{1,2}.cu / k_util.cu
 void launch_synth_bases_g1(uint64_t seed, size_t n, uint32_t *out, cudaStream_t st);
 void launch_synth_bases_g2(uint64_t seed, size_t n, uint32_t *out, cudaStream_t st);

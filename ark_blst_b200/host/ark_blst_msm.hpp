@@ -14,6 +14,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include "../../include/b200msm.h"
 
@@ -69,6 +70,13 @@ struct G1Projective {                    // blst_p1 (Jacobian)
         usize n = nb < ns ? nb : ns;     // infallible and truncating, like arkworks' msm_bigint
         return detail::call<G1Projective>(b200msm_g1, bases, n, reinterpret_cast<const uint64_t *>(bigints), n, 0).unwrap();
     }
+    // CurveGroup::normalize_batch (reference src/g1.rs:536-543); throws on a device error
+    static std::vector<G1Affine> normalize_batch(const G1Projective *v, usize n) {
+        std::vector<G1Affine> out(n);
+        if (b200msm_normalize_batch(B200MSM_G1, reinterpret_cast<const uint64_t *>(v), n, n ? out[0].l : nullptr) != 0)
+            throw std::string("normalize_batch: ") + b200msm_last_error();
+        return out;
+    }
     static G1Projective msm_unchecked(const G1Affine *bases, usize nb, const Scalar *scalars, usize ns) {
         usize n = nb < ns ? nb : ns;
         return msm(bases, n, scalars, n).unwrap();
@@ -87,6 +95,12 @@ struct G2Projective {                    // blst_p2 (Jacobian)
     static G2Projective msm_bigint(const G2Affine *bases, usize nb, const BigInt4 *bigints, usize ns) {
         usize n = nb < ns ? nb : ns;
         return detail::call<G2Projective>(b200msm_g2, bases, n, reinterpret_cast<const uint64_t *>(bigints), n, 0).unwrap();
+    }
+    static std::vector<G2Affine> normalize_batch(const G2Projective *v, usize n) {
+        std::vector<G2Affine> out(n);
+        if (b200msm_normalize_batch(B200MSM_G2, reinterpret_cast<const uint64_t *>(v), n, n ? out[0].l : nullptr) != 0)
+            throw std::string("normalize_batch: ") + b200msm_last_error();
+        return out;
     }
     static G2Projective msm_unchecked(const G2Affine *bases, usize nb, const Scalar *scalars, usize ns) {
         usize n = nb < ns ? nb : ns;

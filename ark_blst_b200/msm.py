@@ -72,6 +72,14 @@ class _Group:
         return cls._call(bases, bigints, False)
 
     @classmethod
+    def normalize_batch(cls, projective):
+        """CurveGroup::normalize_batch(&[Self]) -> Vec<Affine> (reference src/g1.rs:536-543)."""
+        proj = _u64(projective, cls.PROJ_WORDS)
+        out = np.zeros((proj.shape[0], cls.AFFINE_WORDS), dtype=np.uint64)
+        _lib.check(lib.b200msm_normalize_batch(cls.GROUP, _ptr(proj), proj.shape[0], _ptr(out)), "normalize_batch")
+        return out
+
+    @classmethod
     def msm_unchecked(cls, bases, scalars):
         """arkworks' msm_unchecked: truncates to the shorter input instead of erring."""
         bases = _u64(bases, cls.AFFINE_WORDS)

@@ -87,11 +87,22 @@ int b200msm_run_device(int group, const void *d_bases, const void *d_scalars, si
 int b200msm_sum_partials_device(int group, const void *d_partials, int count, void *d_out,
                                 void *stream);
 
+/* Batch normalisation of Jacobian points to affine: replaces the host-side
+ * CurveGroup::normalize_batch → blstrs batch_normalize (reference src/g1.rs:536-543,
+ * src/g2.rs:516-523), the step every caller runs right before msm (src/tests.rs:63).
+ * proj: n × 18|36 u64 (blst_p1 / blst_p2), affine_out: n × 12|24 u64; identity → all-zero. */
+int b200msm_normalize_batch(int group, const uint64_t *proj, size_t n, uint64_t *affine_out);
+int b200msm_normalize_batch_device(int group, const void *d_proj, size_t n, void *d_affine, void *stream);
+
 /* Cumulative count of this library's own kernel launches (CUB sort kernels excluded). */
 unsigned long long b200msm_launch_count(void);
 
 /* Tunables (SURVEY §5 "config/flags"): window width c; 0 = automatic from n. */
 int b200msm_set_window_bits(int c);
+/* Large inputs are cut into passes automatically (sort arrays < 2^32 entries, scratch within the
+ * free HBM) — the chunking the reference left as a TODO (src/gpu.rs:238-239). A non-zero value
+ * forces at most that many points per pass (tests); 0 = automatic. */
+int b200msm_set_max_chunk(size_t max_points_per_pass);
 /* Per-phase device times (ms) of the most recent MSM on this thread's device:
  * [0] digits [1] sort [2] bucket bounds+order [3] accumulate [4] reduce [5] combine [6] total
  * [7] accumulate launches. Filled only when b200msm_set_profiling(1). */

@@ -165,3 +165,20 @@ def test_resident_bases_and_linearity(eng, cref):
     assert cref.affine_equal(0, cref.add(0, a, b), ab)
     assert cref.affine_equal(0, a, cref.msm(0, bases, s, 0))
     assert cref.affine_equal(0, half, cref.msm(0, bases[: n // 2], s[: n // 2], 0))
+
+
+@pytest.mark.parametrize("g2", [0, 1])
+def test_chunked_passes(eng, cref, g2):
+    """the chunking the reference left as a TODO (src/gpu.rs:238-239): forced at small n here"""
+    n = 5000 if not g2 else 1500
+    bases = cref.synth_bases(g2, 41, n)
+    sc = cref.synth_scalars(42, n, True)
+    exp = cref.msm(g2, bases, sc, 1)
+    L = eng._lib.lib
+    for chunk in (n - 1, 1000, 333):
+        assert L.b200msm_set_max_chunk(chunk) == 0
+        try:
+            got = _grp(eng, g2).msm(bases, sc)
+        finally:
+            L.b200msm_set_max_chunk(0)
+        assert cref.affine_equal(g2, got, exp), chunk
