@@ -331,10 +331,14 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases, const void *d_scala
     const bool g2 = group == B200MSM_G2;
     // GPU-side serialisation of the context's scratch arena across streams
     if (cx.busy_valid) CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_busy, 0));
-    size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = (size_t)((double)(free_b + cx.scratch_bytes()) * 0.85);
-    if (g_eng.max_chunk_override) budget = 0;  // tests: force chunking by point count only
+    // cudaMemGetInfo is a slow synchronous driver call (≈0.3–1 ms): only ask when the scratch arena
+    // would have to grow for this n; in steady state the arena already fits
+    size_t budget = ~(size_t)0;
+    if (!g_eng.max_chunk_override && pass_scratch_bytes(n, g2, g_eng.window_override) > cx.scratch_bytes()) {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        budget = (size_t)((double)(free_b + cx.scratch_bytes()) * 0.85);
+    }
     size_t chunks = 1;
     auto too_big = [&](size_t cn) {
         if (g_eng.max_chunk_override) return cn > g_eng.max_chunk_override;
@@ -723,13 +727,13 @@ int b200msm_dbg_field_op(int is_fp2, int op, const uint64_t *a, const uint64_t *
 int b200msm_dbg_point_op(int group, int op, const uint64_t *acc, const uint64_t *q, uint64_t *out, size_t n) {
     if (n == 0) return 0;
     const size_t FB = group == B200MSM_G2 ? 96 : 48;
-    const size_t QB = (op == 0 ? 2 : 4) * FB;
+    const size_t QB = (op == 0 ? 2 : 4) * FB;  // ops 3/4: quad-distributed add / dbl
     uint32_t *dacc = nullptr, *dq = nullptr, *dout = nullptr;
     CUDA_TRY(cudaMalloc(&dacc, n * 4 * FB));
     CUDA_TRY(cudaMalloc(&dq, n * QB));
     CUDA_TRY(cudaMalloc(&dout, n * 3 * FB));
     CUDA_TRY(cudaMemcpy(dacc, acc, n * 4 * FB, cudaMemcpyHostToDevice));
-    if (q && op != 2) CUDA_TRY(cudaMemcpy(dq, q, n * QB, cudaMemcpyHostToDevice));
+    if (q && op != 2 && op != 4) CUDA_TRY(cudaMemcpy(dq, q, n * QB, cudaMemcpyHostToDevice));
     (group == B200MSM_G2 ? launch_dbg_point_op_g2 : launch_dbg_point_op_g1)(op, dacc, dq, dout, n);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(out, dout, n * 3 * FB, cudaMemcpyDeviceToHost));

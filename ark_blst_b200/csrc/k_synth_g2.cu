@@ -9,6 +9,7 @@ void launch_synth_bases_g2(uint64_t seed, size_t n, uint32_t *out, cudaStream_t 
 }
 void launch_dbg_point_op_g2(int op, const uint32_t *acc, const uint32_t *q, uint32_t *out, size_t n) {
     count_launch();
-    k_dbg_point_op<fp2><<<blocks_for(n, 64), 64>>>(op, acc, q, out, n);
+    if (op >= 3) k_dbg_point_op_quad<fp2><<<blocks_for(n * 4, 128), 128>>>(op, acc, q, out, n);
+    else k_dbg_point_op<fp2><<<blocks_for(n, 64), 64>>>(op, acc, q, out, n);
 }
 }  // namespace b200msm

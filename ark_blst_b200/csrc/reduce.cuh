@@ -1,17 +1,17 @@
 // Bucket reduction, window combination and partial-sum kernels (template over the field).
 // All of them are chains of dependent point operations, so they run on quads (quad.cuh): four
-// lanes per chain, every lane holding a replica of the chain state.
+// lanes per chain, lane q owning coordinate q (X, Y, ZZ, ZZZ) of every point in the chain.
 #pragma once
 #include "quad.cuh"
 
 namespace b200msm {
 
-// ---- bucket reduction -----------------------------------------------------------------------
+// ---- bucket reduction, lower part: running sums ----------------------------------------------
 // Weighted sum with 0-based weights, Wsum0(X) = Σ i·X[i], by segments of m:
 //     Wsum0(X) = Σ_s A[s] + m·Wsum0(R),   A[s] = Wsum0(segment s),  R[s] = Sum(segment s)
 // Level k consumes X_k = R_{k-1} and carries C_k[s] = Σ_{seg s} C_{k-1} + M_k·A_k[s] with
-// M_k = Π_{j<k} m_j (a power of two → doublings), so that at the last level (one segment)
-// C = Wsum0(X_0) and R = Sum(X_0); the window value Σ (b+1)·bucket[b] is C + R.
+// M_k = Π_{j<k} m_j (a power of two → doublings), so that Wsum0(X_0) = Σ C_k + M_{k+1}·Wsum0(R_k)
+// and Sum(X_0) = Sum(R_k) hold after every level.
 // Quad (w, s): window w, segment s. Arrays are window-major with the given per-window lengths.
 template <class F>
 __global__ void __launch_bounds__(128)
@@ -22,32 +22,30 @@ k_wsum_level(const uint32_t *__restrict__ X, const uint32_t *__restrict__ Cin, u
     uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     const bool live = t < nseg * nwin;             // quads past the end idle along (warp stays whole)
     if (!live) t = 0;
-    const bool writer = live && (threadIdx.x & 3) == 0;
     uint32_t w = t / nseg, s = t % nseg;
     const uint32_t *x = X + ((size_t)w * len + (size_t)s * m) * PW;
-    xyzz<F> run, acc, tmp;
-    xyzz_set_inf(run);
-    xyzz_set_inf(acc);
-    xyzz<F> nxt;
-    xyzz_load(nxt, x + (size_t)(m - 1) * PW);
+    F run, acc, tmp, nxt;
+    q_set_inf(run);
+    q_set_inf(acc);
+    q_load(nxt, x + (size_t)(m - 1) * PW);
     for (uint32_t j = m; j-- > 0;) {
         tmp = nxt;
-        if (j) xyzz_load(nxt, x + (size_t)(j - 1) * PW);  // prefetch: the global load leaves the chain
-        xyzz_add_quad(run, tmp);
-        if (j) xyzz_add_quad(acc, run);            // warp-uniform: element 0 has weight 0
+        if (j) q_load(nxt, x + (size_t)(j - 1) * PW);  // prefetch: the global load leaves the chain
+        q_add(run, tmp);
+        if (j) q_add(acc, run);                    // warp-uniform: element 0 has weight 0
     }
-    if (writer) xyzz_store(Rout + ((size_t)w * nseg + s) * PW, run);
-    for (int k = 0; k < log2M; k++) xyzz_dbl_quad(acc);
+    if (live) q_store(Rout + ((size_t)w * nseg + s) * PW, run);
+    for (int k = 0; k < log2M; k++) q_dbl(acc);
     if (Cin) {
         const uint32_t *ci = Cin + ((size_t)w * len + (size_t)s * m) * PW;
-        xyzz_load(nxt, ci);
+        q_load(nxt, ci);
         for (uint32_t j = 0; j < m; j++) {
             tmp = nxt;
-            if (j + 1 < m) xyzz_load(nxt, ci + (size_t)(j + 1) * PW);
-            xyzz_add_quad(acc, tmp);
+            if (j + 1 < m) q_load(nxt, ci + (size_t)(j + 1) * PW);
+            q_add(acc, tmp);
         }
     }
-    if (writer) xyzz_store(Cout + ((size_t)w * nseg + s) * PW, acc);
+    if (live) q_store(Cout + ((size_t)w * nseg + s) * PW, acc);
 }
 
 // ---- upper part of the reduction: a log-depth tree instead of more running-sum levels --------
@@ -69,7 +67,6 @@ k_tree_level(const uint32_t *__restrict__ Sin, size_t sin_stride, const uint32_t
     uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     const bool live = idx < ntask;
     if (!live) idx = 0;                            // idle quads tag along so the warp stays whole
-    const bool writer = live && (threadIdx.x & 3) == 0;
     const uint32_t w = idx / (n2 * per), rem = idx % (n2 * per);
     const uint32_t t = rem / per, r = rem % per;
     const uint32_t *pa, *pb;
@@ -90,13 +87,13 @@ k_tree_level(const uint32_t *__restrict__ Sin, size_t sin_stride, const uint32_t
         pb = cp + (size_t)(2 * t + 1) * PW;
         pd = Cout + ((size_t)w * out_stride + t) * PW;
     }
-    xyzz<F> a, b;
-    xyzz_load(a, pa);
-    xyzz_load(b, pb);
-    if (writer && r == (uint32_t)j)                // V'_j = S_r
-        xyzz_store(Vout + ((size_t)w * out_stride + (size_t)t * (j + 1) + j) * PW, b);
-    xyzz_add_quad(a, b);
-    if (writer) xyzz_store(pd, a);
+    F a, b;
+    q_load(a, pa);
+    q_load(b, pb);
+    if (live && r == (uint32_t)j)                  // V'_j = S_r
+        q_store(Vout + ((size_t)w * out_stride + (size_t)t * (j + 1) + j) * PW, b);
+    q_add(a, b);
+    if (live) q_store(pd, a);
 }
 
 // Per window: value_w = C_root + 2^log2M·(Σ_k 2^k V_k) + S_root (one quad per window, Horner over
@@ -106,60 +103,54 @@ template <class F>
 __global__ void __launch_bounds__(128)
 k_combine(const uint32_t *__restrict__ Sroot, const uint32_t *__restrict__ V, const uint32_t *__restrict__ Croot,
           size_t stride, int logS, int log2M, int nwin, int c, uint32_t *__restrict__ wsum, uint32_t *__restrict__ out) {
-    constexpr int PW = 4 * field_words<F>::value;
+    constexpr int W = field_words<F>::value;
+    constexpr int PW = 4 * W;
     const int qd = threadIdx.x >> 2;
-    xyzz<F> acc, a;
+    F acc, a;
     for (int base = 0; base < nwin; base += 32) {  // block-uniform trip count
         const int w = base + qd < nwin ? base + qd : 0;  // surplus quads recompute window 0
-        xyzz_set_inf(acc);
+        q_set_inf(acc);
         const uint32_t *v = V + (size_t)w * stride * PW;
         for (int k = logS - 1; k >= 0; k--) {      // T = Σ_k 2^k V_k
-            xyzz_dbl_quad(acc);
-            xyzz_load(a, v + (size_t)k * PW);
-            xyzz_add_quad(acc, a);
+            q_dbl(acc);
+            q_load(a, v + (size_t)k * PW);
+            q_add(acc, a);
         }
-        for (int k = 0; k < log2M; k++) xyzz_dbl_quad(acc);
+        for (int k = 0; k < log2M; k++) q_dbl(acc);
         if (Croot) {
-            xyzz_load(a, Croot + (size_t)w * stride * PW);
-            xyzz_add_quad(acc, a);
+            q_load(a, Croot + (size_t)w * stride * PW);
+            q_add(acc, a);
         }
-        xyzz_load(a, Sroot + (size_t)w * stride * PW);
-        xyzz_add_quad(acc, a);
-        if (base + qd < nwin && (threadIdx.x & 3) == 0) xyzz_store(wsum + (size_t)(base + qd) * PW, acc);
+        q_load(a, Sroot + (size_t)w * stride * PW);
+        q_add(acc, a);
+        if (base + qd < nwin) q_store(wsum + (size_t)(base + qd) * PW, acc);
     }
     __syncthreads();                               // window sums visible to warp 0
     if (threadIdx.x >= 32) return;                 // warp 0 finishes (its 8 quads in lock-step)
-    xyzz_set_inf(acc);
+    q_set_inf(acc);
     for (int ww = nwin - 1; ww >= 0; ww--) {
-        for (int k = 0; k < c; k++) xyzz_dbl_quad(acc);
-        xyzz_load(a, wsum + (size_t)ww * PW);
-        xyzz_add_quad(acc, a);
+        for (int k = 0; k < c; k++) q_dbl(acc);
+        q_load(a, wsum + (size_t)ww * PW);
+        q_add(acc, a);
     }
-    if (threadIdx.x == 0) {
-        jac<F> r;
-        xyzz_to_jac(r, acc);
-        jac_store(out, r);
-    }
+    F r = q_to_jac(acc);
+    if (threadIdx.x < 3) f_store(out + threadIdx.x * W, r);
 }
 
 // out = Σ partial_i (Jacobian in, Jacobian out): the final addition after the gather of per-GPU
-// partial sums (or of the per-shard partials of a chunked single-GPU run). One quad.
+// partial sums (or of the per-pass partials of a chunked run). One warp; quad 0 writes.
 template <class F>
 __global__ void k_sum_partials(const uint32_t *__restrict__ partials, int count, uint32_t *__restrict__ out) {
-    constexpr int JW = 3 * field_words<F>::value;
-    if (blockIdx.x) return;                        // one warp; quad 0 writes
-    xyzz<F> acc, a;
-    jac<F> j;
-    xyzz_set_inf(acc);
+    constexpr int W = field_words<F>::value;
+    if (blockIdx.x) return;
+    F acc;
+    q_set_inf(acc);
     for (int i = 0; i < count; i++) {
-        jac_load(j, partials + (size_t)i * JW);
-        jac_to_xyzz(a, j);
-        xyzz_add_quad(acc, a);
+        F a = q_load_jac<F>(partials + (size_t)i * 3 * W);
+        q_add(acc, a);
     }
-    if (threadIdx.x == 0) {
-        xyzz_to_jac(j, acc);
-        jac_store(out, j);
-    }
+    F r = q_to_jac(acc);
+    if (threadIdx.x < 3) f_store(out + threadIdx.x * W, r);
 }
 
 }  // namespace b200msm

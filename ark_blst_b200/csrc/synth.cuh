@@ -6,7 +6,7 @@
 // matching the reference benches' "random affine bases × random Fr" shape (benches/group.rs:18-26)
 // while keeping the discrete logs known, so Σ sᵢPᵢ = (Σ sᵢkᵢ)·G can be checked at any n.
 #pragma once
-#include "ec.cuh"
+#include "quad.cuh"
 #include "scalar.cuh"
 
 namespace b200msm {
@@ -199,5 +199,25 @@ __global__ void k_dbg_point_op(int op, const uint32_t *acc_in, const uint32_t *q
     jac_store(out + i * 3 * W, r);
 }
 
+
+// quad-distributed variants of the same hooks: op 3 = q_add (XYZZ + XYZZ), op 4 = q_dbl
+template <class F>
+__global__ void __launch_bounds__(128)
+k_dbg_point_op_quad(int op, const uint32_t *acc_in, const uint32_t *qin, uint32_t *out, size_t n) {
+    constexpr int W = field_words<F>::value;
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const bool live = i < n;
+    if (!live) i = 0;
+    F a, b;
+    q_load(a, acc_in + i * 4 * W);
+    if (op == 3) {
+        q_load(b, qin + i * 4 * W);
+        q_add(a, b);
+    } else {
+        q_dbl(a);
+    }
+    F r = q_to_jac(a);
+    if (live && (threadIdx.x & 3) < 3) f_store(out + i * 3 * W + (threadIdx.x & 3) * W, r);
+}
 
 }  // namespace b200msm

@@ -1,4 +1,5 @@
-"""XYZZ point kernels (madd / add / dbl) against the oracle, including every exceptional case."""
+"""XYZZ point kernels (madd / add / dbl, and the quad-distributed add / dbl = ops 3 / 4) against the
+oracle, including every exceptional case."""
 import random
 
 import numpy as np
@@ -36,7 +37,7 @@ def _cases(C, rng, n):
 
 
 @pytest.mark.parametrize("g2", [0, 1])
-@pytest.mark.parametrize("op", [0, 1, 2])
+@pytest.mark.parametrize("op", [0, 1, 2, 3, 4])
 def test_point_ops(eng, g2, op):
     C = curve(g2)
     rng = random.Random(300 + 10 * g2 + op)
@@ -52,6 +53,6 @@ def test_point_ops(eng, g2, op):
     rc = eng._lib.lib.b200msm_dbg_point_op(g2, op, acc.ctypes.data_as(u), q.ctypes.data_as(u), out.ctypes.data_as(u), n)
     assert rc == 0, eng._lib.lib.b200msm_last_error()
     for i in range(n):
-        exp = C.add_affine(pts[i], qs[i]) if op < 2 else C.add_affine(pts[i], pts[i])
+        exp = C.add_affine(pts[i], qs[i]) if op in (0, 1, 3) else C.add_affine(pts[i], pts[i])
         got = C.jac_from_limbs([int(v) for v in out[i]])
         assert C.eq(got, exp), (i, op)
