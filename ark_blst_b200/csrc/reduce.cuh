@@ -14,7 +14,7 @@ namespace b200msm {
 // and Sum(X_0) = Sum(R_k) hold after every level.
 // Quad (w, s): window w, segment s. Arrays are window-major with the given per-window lengths.
 template <class F>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (field_words<F>::value == 12 ? 3 : 2))  // G1: 168 regs, no spills
 k_wsum_level(const uint32_t *__restrict__ X, const uint32_t *__restrict__ Cin, uint32_t len, uint32_t m,
              int log2M, uint32_t nwin, uint32_t *__restrict__ Rout, uint32_t *__restrict__ Cout) {
     constexpr int PW = 4 * field_words<F>::value;  // words per XYZZ point
