@@ -38,7 +38,7 @@ def test_synth_matches_oracle(eng, cref):
         assert np.array_equal(sc.cpu().numpy().view(np.uint64), cref.synth_scalars(456, n, False))
 
 
-@pytest.mark.parametrize("g2,logn", [(0, 16), (0, 20), (1, 18)])
+@pytest.mark.parametrize("g2,logn", [(0, 16), (0, 20), (1, 18), (1, 20)])
 def test_dlog_closed_form(eng, cref, g2, logn):
     """Σ sᵢ·(kᵢ·G) = (Σ sᵢkᵢ mod r)·G at BASELINE sizes"""
     import torch
