@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -67,7 +68,6 @@ struct DevBuf {
 struct Plan {
     int c = 0, nwin = 0;
     uint32_t nbw = 0, nb = 0;  // buckets per window, total
-    int key_bits = 0;
 };
 
 // SURVEY §8(d) work model, minimised over c; the same expression the roofline numerator uses.
@@ -90,14 +90,15 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
     cudaEvent_t ev_scalars = nullptr, ev_bases = nullptr, ev_busy = nullptr, ev_fork = nullptr, ev_join = nullptr;
     bool busy_valid = false;
-    DevBuf bases, scalars, keys[2], vals[2], cubtmp, start, cnt[2], ord[2], buckets, lvlR[2], lvlC[2], out;
-    DevBuf hvy_hdr, hvy_buckets, hvy_tasks, hvy_partials, treeS[2], treeV[2], treeC[2], wsum, chunk_partials, norm_in, norm_out;
+    size_t fits_n[2] = {0, 0};  // largest n per group that already ran as a single pass (arena is big enough)
+    DevBuf bases, scalars, digits, vals, start, cnt, ord, buckets, lvlR[2], lvlC[2], out;
+    DevBuf hvy_hdr, hvy_buckets, hvy_tasks, hvy_partials, treeS[2], treeV[2], treeC[2], wsum, chunk_partials, norm_in, norm_out, tile_sums, size_hist;
     cudaEvent_t ev[8] = {};
     double phase_ms[8] = {};
     bool phase_pending = false;
     int sm_count = 0;
     std::vector<DevBuf *> scratch() {
-        return {&keys[0], &keys[1], &vals[0], &vals[1], &cubtmp, &start, &cnt[0], &cnt[1], &ord[0], &ord[1], &buckets,
+        return {&digits, &vals, &start, &cnt, &ord, &buckets,
                 &lvlR[0], &lvlR[1], &lvlC[0], &lvlC[1], &hvy_hdr, &hvy_buckets, &hvy_tasks, &hvy_partials, &treeS[0],
                 &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum};
     }
@@ -107,9 +108,8 @@ struct DeviceCtx {
         return s;
     }
     void release_all() {
-        for (DevBuf *b : {&bases, &scalars, &keys[0], &keys[1], &vals[0], &vals[1], &cubtmp, &start, &cnt[0], &cnt[1],
-                          &ord[0], &ord[1], &buckets, &lvlR[0], &lvlR[1], &lvlC[0], &lvlC[1], &out, &hvy_hdr, &hvy_buckets,
-                          &hvy_tasks, &hvy_partials, &treeS[0], &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum, &chunk_partials, &norm_in, &norm_out})
+        for (DevBuf *b : {&bases, &scalars, &digits, &vals, &start, &cnt, &ord, &buckets, &lvlR[0], &lvlR[1], &lvlC[0], &lvlC[1], &out, &hvy_hdr, &hvy_buckets,
+                          &hvy_tasks, &hvy_partials, &treeS[0], &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum, &chunk_partials, &norm_in, &norm_out, &tile_sums, &size_hist})
             b->release();
     }
 };
@@ -119,7 +119,7 @@ struct Engine {
     bool inited = false;
     std::vector<std::unique_ptr<DeviceCtx>> ctx;
     int window_override = 0;
-    size_t max_chunk_override = 0;  // tests: force chunked execution at small n
+    size_t max_chunk_override = 0;
     bool profiling = false;
 };
 Engine g_eng;
@@ -194,18 +194,16 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     pl.nwin = (256 + pl.c - 1) / pl.c;  // c·W ≥ 256 > 255 = |r|: the top Booth carry stays inside
     pl.nbw = 1u << (pl.c - 1);
     pl.nb = pl.nbw * (uint32_t)pl.nwin;
-    pl.key_bits = 1;
-    while ((1ull << pl.key_bits) <= pl.nb) pl.key_bits++;  // keys run 0..nb inclusive (sentinel)
     const size_t m = n * (size_t)pl.nwin;
     const bool prof = g_eng.profiling;
     int evi = 0;
     auto mark = [&]() { if (prof) cudaEventRecord(cx.ev[evi++], st); };
 
+    if (int rc = cx.digits.reserve(m * 4)) return rc;
+    if (int rc = cx.vals.reserve(m * 4)) return rc;
+    if (int rc = cx.cnt.reserve((size_t)pl.nb * 4)) return rc;
+    if (int rc = cx.ord.reserve((size_t)pl.nb * 4)) return rc;
     for (int i = 0; i < 2; i++) {
-        if (int rc = cx.keys[i].reserve(m * 4)) return rc;
-        if (int rc = cx.vals[i].reserve(m * 4)) return rc;
-        if (int rc = cx.cnt[i].reserve((size_t)pl.nb * 4)) return rc;
-        if (int rc = cx.ord[i].reserve((size_t)pl.nb * 4)) return rc;
         size_t lvl = (size_t)pl.nwin * std::max<size_t>(1, pl.nbw / 32) * PB;
         if (int rc = cx.lvlR[i].reserve(lvl)) return rc;
         if (int rc = cx.lvlC[i].reserve(lvl)) return rc;
@@ -225,30 +223,20 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     if (int rc = cx.hvy_buckets.reserve(max_heavy * 12)) return rc;
     if (int rc = cx.hvy_tasks.reserve(max_tasks * 8)) return rc;
     if (int rc = cx.hvy_partials.reserve(max_tasks * PB)) return rc;
-    uint32_t *keys[2] = {cx.keys[0].as<uint32_t>(), cx.keys[1].as<uint32_t>()};
-    uint32_t *vals[2] = {cx.vals[0].as<uint32_t>(), cx.vals[1].as<uint32_t>()};
-    uint32_t *cnt[2] = {cx.cnt[0].as<uint32_t>(), cx.cnt[1].as<uint32_t>()};
-    uint32_t *ord[2] = {cx.ord[0].as<uint32_t>(), cx.ord[1].as<uint32_t>()};
+    uint32_t *vals = cx.vals.as<uint32_t>(), *ord = cx.ord.as<uint32_t>();
     uint32_t *start = cx.start.as<uint32_t>();
-    const int cnt_bits = 12;  // sizes above 4095 all sort first; finer order buys nothing
-    size_t tmp1 = 0, tmp2 = 0;
-    CUDA_TRY(sort_pairs(nullptr, &tmp1, keys[0], keys[1], vals[0], vals[1], m, pl.key_bits, false, nullptr, st));
-    CUDA_TRY(sort_pairs(nullptr, &tmp2, cnt[0], cnt[1], ord[0], ord[1], pl.nb, cnt_bits, true, nullptr, st));
-    if (int rc = cx.cubtmp.reserve(std::max(tmp1, tmp2))) return rc;
+    if (int rc = cx.tile_sums.reserve(((size_t)pl.nb / 2048 + 4) * 4)) return rc;
+    if (int rc = cx.size_hist.reserve(2 * 4096 * 4)) return rc;
 
     mark();
-    // 1. signed window digits → (bucket key, point index|sign)
-    launch_digits(d_scalars, n, mont, pl.c, pl.nwin, keys[0], vals[0], st);
+    // 1+2. canonical scalars → window digits, per-bucket histogram, scan → bucket offsets, scatter
+    //      of the point indices (a counting sort on the bucket id; zero digits are dropped)
+    launch_group_by_bucket(d_scalars, n, mont, pl.c, pl.nwin, pl.nb, cx.digits.as<uint32_t>(), cx.cnt.as<uint32_t>(), start,
+                           cx.tile_sums.as<uint32_t>(), vals, st);
     mark();
-    // 2. radix sort by bucket key
-    int sel = 0;
-    CUDA_TRY(sort_pairs(cx.cubtmp.p, &tmp1, keys[0], keys[1], vals[0], vals[1], m, pl.key_bits, false, &sel, st));
     mark();
-    // 3. bucket offsets, then buckets in decreasing-size order
-    launch_bounds(keys[sel], m, pl.nb, start, st);
-    launch_counts(start, pl.nb, (1u << cnt_bits) - 1, cnt[0], ord[0], st);
-    int osel = 0;
-    CUDA_TRY(sort_pairs(cx.cubtmp.p, &tmp2, cnt[0], cnt[1], ord[0], ord[1], pl.nb, cnt_bits, true, &osel, st));
+    // 3. buckets in decreasing-size order (sizes above 4095 all sort first)
+    launch_order_by_size(start, pl.nb, cx.size_hist.as<uint32_t>(), ord, st);
     mark();
     // 4. bucket accumulation
     CUDA_TRY(cudaMemsetAsync(cx.hvy_hdr.p, 0, 16, st));
@@ -257,11 +245,11 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     // the SMs the other leaves idle at its tail
     CUDA_TRY(cudaEventRecord(cx.ev_fork, st));
     CUDA_TRY(cudaStreamWaitEvent(cx.aux_stream, cx.ev_fork, 0));
-    (g2 ? launch_heavy_g2 : launch_heavy_g1)(d_bases, vals[sel], start, ord[osel], pl.nb, heavy_thr, cx.hvy_hdr.p,
+    (g2 ? launch_heavy_g2 : launch_heavy_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, cx.hvy_hdr.p,
                                              cx.hvy_buckets.p, cx.hvy_tasks.p, cx.hvy_partials.as<uint32_t>(),
                                              cx.buckets.as<uint32_t>(), cx.sm_count * 4, cx.aux_stream);
     CUDA_TRY(cudaEventRecord(cx.ev_join, cx.aux_stream));
-    (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals[sel], start, ord[osel], pl.nb, heavy_thr,
+    (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr,
                                                        cx.buckets.as<uint32_t>(), st);
     CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_join, 0));
     mark();
@@ -318,7 +306,7 @@ size_t pass_scratch_bytes(size_t n, bool g2, int c_override) {
     c = std::max(2, std::min(c, 24));
     size_t nwin = (256 + c - 1) / c, nb = nwin << (c - 1), m = n * nwin;
     size_t PB = g2 ? 384 : 192;
-    return m * 16 + nb * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + (64u << 20);
+    return m * 8 + nb * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + (64u << 20);
 }
 
 // The whole MSM on one device: one pass when it fits, otherwise the chunking the reference left
@@ -331,10 +319,10 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases, const void *d_scala
     const bool g2 = group == B200MSM_G2;
     // GPU-side serialisation of the context's scratch arena across streams
     if (cx.busy_valid) CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_busy, 0));
-    // cudaMemGetInfo is a slow synchronous driver call (≈0.3–1 ms): only ask when the scratch arena
-    // would have to grow for this n; in steady state the arena already fits
+    // cudaMemGetInfo is a slow synchronous driver call (≈0.3–1 ms): only ask for sizes that have
+    // not already run as a single pass on this context (the grow-only arena then fits)
     size_t budget = ~(size_t)0;
-    if (!g_eng.max_chunk_override && pass_scratch_bytes(n, g2, g_eng.window_override) > cx.scratch_bytes()) {
+    if (!g_eng.max_chunk_override && n > cx.fits_n[g2 ? 1 : 0]) {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         budget = (size_t)((double)(free_b + cx.scratch_bytes()) * 0.85);
@@ -353,6 +341,7 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases, const void *d_scala
     int rc = 0;
     if (chunks == 1) {
         rc = run_pass(group, cx, d_bases, d_scalars, n, mont, d_out, st, bases_ready);
+        if (!rc && !g_eng.max_chunk_override && g_eng.window_override == 0) cx.fits_n[g2 ? 1 : 0] = std::max(cx.fits_n[g2 ? 1 : 0], n);
     } else {
         const size_t AB = g2 ? 192 : 96, JB = g2 ? 288 : 144;
         if ((rc = cx.chunk_partials.reserve(chunks * JB))) return rc;

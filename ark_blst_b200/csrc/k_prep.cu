@@ -1,30 +1,12 @@
-// Scalar preparation kernels: window digits, bucket offsets, bucket-size keys, and the device
-// radix sorts (CUB DeviceRadixSort on sm_100a; see DESIGN.md for why the sort is not the bottleneck).
-#include <cub/device/device_radix_sort.cuh>
+// Scalar preparation kernels: window digits, grouping of the point indices by bucket (a counting
+// sort on the bucket id — the pipeline's "radix sort by bucket", hand-written: no library kernel
+// runs on the MSM path) and the ordering of the buckets by size.
 
 #include "launch.h"
 #include "scalar.cuh"
 
 namespace b200msm {
 
-// keys/vals are window-major: entry (w, i) at w·n + i, so every store is coalesced.
-__global__ void __launch_bounds__(256)
-k_digits(const uint32_t *__restrict__ scalars, size_t n, int mont, int c, int nwin,
-         uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t s[8];
-    load_scalar(s, scalars, i, mont);
-    const uint32_t nbw = 1u << (c - 1);
-    const uint32_t sentinel = nbw * (uint32_t)nwin;  // zero digits sort past every real bucket
-    for (int w = 0; w < nwin; w++) {
-        int d = booth_digit(s, w, c);
-        uint32_t neg = d < 0;
-        uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
-        keys[(size_t)w * n + i] = mag ? (uint32_t)w * nbw + (mag - 1) : sentinel;
-        vals[(size_t)w * n + i] = (uint32_t)i | (neg << 31);
-    }
-}
 __global__ void k_digits_dbg(const uint32_t *__restrict__ scalars, size_t n, int mont, int c, int nwin,
                              int *__restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -34,53 +16,194 @@ __global__ void k_digits_dbg(const uint32_t *__restrict__ scalars, size_t n, int
     for (int w = 0; w < nwin; w++) out[(size_t)w * n + i] = booth_digit(s, w, c);
 }
 
-// start[b] = first sorted position whose key ≥ b, for b in [0, nb+1]; m = number of entries.
-// Bucket b owns [start[b], start[b+1]); bucket nb is the sentinel (zero digits), start[nb+1] = m.
-// Position j opens every bucket in (keys[j-1], keys[j]]; each b is written by exactly one j.
+// ---- bucket grouping without a general-purpose sort -------------------------------------------
+// Only the grouping by bucket matters (order inside a bucket is irrelevant to the sum), so the
+// "radix sort by bucket" is a counting sort on the full bucket id in two passes: (1) canonicalise
+// the scalar, write its window digits (window-major) and histogram them (one RED per non-zero
+// digit), exclusive scan, (2) scatter point indices to start[b] + cursor[b]++, window by window.
+// Zero digits are dropped instead of being carried to a sentinel bucket, and the scan directly
+// yields the bucket offsets.
 __global__ void __launch_bounds__(256)
-k_bounds(const uint32_t *__restrict__ keys, size_t m, uint32_t nb, uint32_t *__restrict__ start) {
-    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j > m) return;
-    uint32_t lo = j ? keys[j - 1] + 1 : 0;
-    uint32_t hi = j < m ? keys[j] : nb + 1;
-    for (uint32_t b = lo; b <= hi; b++) start[b] = (uint32_t)j;
+k_hist(const uint32_t *__restrict__ scalars, size_t n, int mont, int c, int nwin, uint32_t *__restrict__ dig,
+       uint32_t *__restrict__ count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    load_scalar(s, scalars, i, mont);
+    const uint32_t nbw = 1u << (c - 1);
+    for (int w = 0; w < nwin; w++) {
+        int d = booth_digit(s, w, c);
+        uint32_t neg = d < 0;
+        uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
+        dig[(size_t)w * n + i] = (mag << 1) | neg;   // window-major: coalesced; 0 = zero digit
+        if (mag) atomicAdd(&count[(uint32_t)w * nbw + (mag - 1)], 1u);
+    }
 }
-// sort key for the size ordering: min(count, 2^bits - 1)
+// grid (point blocks, windows): blocks are dispatched window after window, so at any time the
+// scattered stores fall into one window's slice of vals (n·4 bytes) and its cursors — a working
+// set that stays in the 126 MB L2 up to n = 2^24 instead of spraying the whole n·W·4-byte array
 __global__ void __launch_bounds__(256)
-k_counts(const uint32_t *__restrict__ start, uint32_t nb, uint32_t clampv,
-         uint32_t *__restrict__ cnt, uint32_t *__restrict__ ids) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    uint32_t c = start[b + 1] - start[b];
-    cnt[b] = c < clampv ? c : clampv;
-    ids[b] = b;
+k_scatter(const uint32_t *__restrict__ dig, size_t n, int c, const uint32_t *__restrict__ start,
+          uint32_t *__restrict__ cursor, uint32_t *__restrict__ vals) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t w = blockIdx.y;
+    uint32_t d = dig[(size_t)w * n + i];
+    if (!d) return;
+    uint32_t bk = (w << (c - 1)) + ((d >> 1) - 1);
+    uint32_t pos = start[bk] + atomicAdd(&cursor[bk], 1u);
+    vals[pos] = (uint32_t)i | (d << 31);
 }
 
-
-void launch_digits(const uint32_t *scalars, size_t n, int mont, int c, int nwin, uint32_t *keys, uint32_t *vals,
-                   cudaStream_t st) {
-    count_launch();
-    k_digits<<<blocks_for(n, 256), 256, 0, st>>>(scalars, n, mont, c, nwin, keys, vals);
+// exclusive scan of n u32 (n up to 2^27): 2048 elements per block, block sums scanned by one block
+constexpr int SCAN_ITEMS = 8, SCAN_THREADS = 256, SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total) {
+    __shared__ uint32_t wsum[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < SCAN_THREADS / 32 ? wsum[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        if (lane < SCAN_THREADS / 32) wsum[lane] = w;
+    }
+    __syncthreads();
+    uint32_t base = wid ? wsum[wid - 1] : 0;
+    *total = wsum[SCAN_THREADS / 32 - 1];
+    __syncthreads();
+    return base + x - v;
 }
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_tiles(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n, uint32_t *__restrict__ tile_sums) {
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = base + k < n ? in[base + k] : 0;
+        sum += v[k];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(sum, &total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+    }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_sums(uint32_t *__restrict__ tile_sums, size_t ntiles, uint32_t *__restrict__ grand_total) {
+    uint32_t carry = 0;
+    for (size_t base = 0; base < ntiles; base += SCAN_THREADS) {
+        size_t i = base + threadIdx.x;
+        uint32_t v = i < ntiles ? tile_sums[i] : 0, total;
+        uint32_t ex = block_exclusive_scan(v, &total);
+        if (i < ntiles) tile_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+// out[i] += tile offset; also out[n] = out[n+1] = grand total (start[nb] and start[nb+1])
+__global__ void __launch_bounds__(256)
+k_scan_add(uint32_t *__restrict__ out, size_t n, const uint32_t *__restrict__ tile_sums, const uint32_t *__restrict__ grand_total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += tile_sums[i / SCAN_TILE];
+    if (i == 0) { out[n] = *grand_total; out[n + 1] = *grand_total; }
+}
+
+// ---- buckets ordered by decreasing size: one counting-sort pass on min(count, SIZE_BINS-1) ------
+constexpr int SIZE_BINS = 4096, SIZE_THREADS = 256, SIZE_ITEMS = 4;
+__global__ void __launch_bounds__(SIZE_THREADS)
+k_size_hist(const uint32_t *__restrict__ start, uint32_t nb, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t lh[SIZE_BINS];
+    for (int k = threadIdx.x; k < SIZE_BINS; k += SIZE_THREADS) lh[k] = 0;
+    __syncthreads();
+    uint32_t b0 = (blockIdx.x * SIZE_THREADS + threadIdx.x) * SIZE_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SIZE_ITEMS; k++) {
+        uint32_t b = b0 + k;
+        if (b < nb) {
+            uint32_t cn = start[b + 1] - start[b];
+            atomicAdd(&lh[cn < SIZE_BINS - 1 ? cn : SIZE_BINS - 1], 1u);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < SIZE_BINS; k += SIZE_THREADS)
+        if (lh[k]) atomicAdd(&hist[k], lh[k]);
+}
+// descending exclusive scan of the size histogram: binstart[s] = #buckets with size bin > s
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_size_scan(const uint32_t *__restrict__ hist, uint32_t *__restrict__ binstart) {
+    uint32_t carry = 0;
+    for (int base = 0; base < SIZE_BINS; base += SCAN_THREADS) {
+        int r = base + threadIdx.x;                // rank in descending order
+        uint32_t v = hist[SIZE_BINS - 1 - r], total;
+        uint32_t ex = block_exclusive_scan(v, &total);
+        binstart[SIZE_BINS - 1 - r] = carry + ex;
+        carry += total;
+    }
+}
+__global__ void __launch_bounds__(SIZE_THREADS)
+k_size_scatter(const uint32_t *__restrict__ start, uint32_t nb, uint32_t *__restrict__ bincursor,
+               uint32_t *__restrict__ order) {
+    __shared__ uint32_t lh[SIZE_BINS];   // local count, then global base of this block's run per bin
+    for (int k = threadIdx.x; k < SIZE_BINS; k += SIZE_THREADS) lh[k] = 0;
+    __syncthreads();
+    uint32_t b0 = (blockIdx.x * SIZE_THREADS + threadIdx.x) * SIZE_ITEMS;
+    uint32_t bin[SIZE_ITEMS], rank[SIZE_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SIZE_ITEMS; k++) {
+        uint32_t b = b0 + k;
+        bin[k] = 0xffffffffu;
+        if (b < nb) {
+            uint32_t cn = start[b + 1] - start[b];
+            bin[k] = cn < SIZE_BINS - 1 ? cn : SIZE_BINS - 1;
+            rank[k] = atomicAdd(&lh[bin[k]], 1u);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < SIZE_BINS; k += SIZE_THREADS)
+        if (lh[k]) lh[k] = atomicAdd(&bincursor[k], lh[k]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SIZE_ITEMS; k++)
+        if (bin[k] != 0xffffffffu) order[lh[bin[k]] + rank[k]] = b0 + k;
+}
+
+void launch_group_by_bucket(const uint32_t *scalars, size_t n, int mont, int c, int nwin, uint32_t nb, uint32_t *dig,
+                            uint32_t *count, uint32_t *start, uint32_t *tile_sums, uint32_t *vals, cudaStream_t st) {
+    for (int k = 0; k < 7; k++) count_launch();
+    cudaMemsetAsync(count, 0, (size_t)nb * 4, st);
+    k_hist<<<blocks_for(n, 256), 256, 0, st>>>(scalars, n, mont, c, nwin, dig, count);
+    size_t ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(count, start, nb, tile_sums);
+    k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, ntiles, tile_sums + ntiles);
+    k_scan_add<<<blocks_for(nb, 256), 256, 0, st>>>(start, nb, tile_sums, tile_sums + ntiles);
+    cudaMemsetAsync(count, 0, (size_t)nb * 4, st);   // reused as the scatter cursors
+    k_scatter<<<dim3(blocks_for(n, 256), (unsigned)nwin), 256, 0, st>>>(dig, n, c, start, count, vals);
+}
+// hist: 2·SIZE_BINS u32 of scratch
+void launch_order_by_size(const uint32_t *start, uint32_t nb, uint32_t *hist, uint32_t *order, cudaStream_t st) {
+    for (int k = 0; k < 3; k++) count_launch();
+    cudaMemsetAsync(hist, 0, SIZE_BINS * 4, st);
+    unsigned blocks = blocks_for(nb, SIZE_THREADS * SIZE_ITEMS);
+    k_size_hist<<<blocks, SIZE_THREADS, 0, st>>>(start, nb, hist);
+    k_size_scan<<<1, SCAN_THREADS, 0, st>>>(hist, hist + SIZE_BINS);
+    k_size_scatter<<<blocks, SIZE_THREADS, 0, st>>>(start, nb, hist + SIZE_BINS, order);
+}
+
 void launch_digits_dbg(const uint32_t *scalars, size_t n, int mont, int c, int nwin, int *out, cudaStream_t st) {
     count_launch();
     k_digits_dbg<<<blocks_for(n, 256), 256, 0, st>>>(scalars, n, mont, c, nwin, out);
 }
-void launch_bounds(const uint32_t *keys, size_t m, uint32_t nb, uint32_t *start, cudaStream_t st) {
-    count_launch();
-    k_bounds<<<blocks_for(m + 1, 256), 256, 0, st>>>(keys, m, nb, start);
-}
-void launch_counts(const uint32_t *start, uint32_t nb, uint32_t clampv, uint32_t *cnt, uint32_t *ids, cudaStream_t st) {
-    count_launch();
-    k_counts<<<blocks_for(nb, 256), 256, 0, st>>>(start, nb, clampv, cnt, ids);
-}
-cudaError_t sort_pairs(void *tmp, size_t *tmp_bytes, uint32_t *k0, uint32_t *k1, uint32_t *v0, uint32_t *v1, size_t m,
-                       int end_bit, bool descending, int *sel, cudaStream_t st) {
-    cub::DoubleBuffer<uint32_t> dk(k0, k1), dv(v0, v1);
-    cudaError_t e = descending ? cub::DeviceRadixSort::SortPairsDescending(tmp, *tmp_bytes, dk, dv, m, 0, end_bit, st)
-                               : cub::DeviceRadixSort::SortPairs(tmp, *tmp_bytes, dk, dv, m, 0, end_bit, st);
-    if (sel) *sel = dk.selector;
-    return e;
-}
-
 }  // namespace b200msm

@@ -9,16 +9,13 @@
 namespace b200msm {
 
 // k_prep.cu
-void launch_digits(const uint32_t *scalars, size_t n, int mont, int c, int nwin, uint32_t *keys, uint32_t *vals,
-                   cudaStream_t st);
 void launch_digits_dbg(const uint32_t *scalars, size_t n, int mont, int c, int nwin, int *out, cudaStream_t st);
-void launch_bounds(const uint32_t *keys, size_t m, uint32_t nb, uint32_t *start, cudaStream_t st);
-void launch_counts(const uint32_t *start, uint32_t nb, uint32_t clampv, uint32_t *cnt, uint32_t *ids, cudaStream_t st);
-// radix sort of (key,val) u32 pairs on bits [0,end_bit). Double buffers: result lands in
-// k[*sel]/v[*sel]. tmp == nullptr → size query only.
-cudaError_t sort_pairs(void *tmp, size_t *tmp_bytes, uint32_t *k0, uint32_t *k1, uint32_t *v0, uint32_t *v1, size_t m,
-                       int end_bit, bool descending, int *sel, cudaStream_t st);
-
+// hand-written grouping by bucket (counting sort on the bucket id, built from the scalars):
+// dig: n·nwin u32, count: nb u32, start: nb+2 u32, tile_sums: nb/2048+2 u32, vals: ≥ n·nwin u32
+void launch_group_by_bucket(const uint32_t *scalars, size_t n, int mont, int c, int nwin, uint32_t nb, uint32_t *dig,
+                            uint32_t *count, uint32_t *start, uint32_t *tile_sums, uint32_t *vals, cudaStream_t st);
+// bucket ids in decreasing-size order (counting sort on the clamped size); hist: 8192 u32 scratch
+void launch_order_by_size(const uint32_t *start, uint32_t nb, uint32_t *hist, uint32_t *order, cudaStream_t st);
 // k_accumulate_g{1,2}.cu
 constexpr uint32_t HEAVY_CHUNK = 4096;  // entries per block task of a heavy bucket
 void launch_accumulate_g1(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
