@@ -34,6 +34,7 @@ SIGNATURES = {
     "b200msm_normalize_batch_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, vp, vp]),
     "b200msm_launch_count": (ctypes.c_ulonglong, []),
     "b200msm_set_window_bits": (ctypes.c_int, [ctypes.c_int]),
+    "b200msm_set_glv": (ctypes.c_int, [ctypes.c_int]),
     "b200msm_set_max_chunk": (ctypes.c_int, [ctypes.c_size_t]),
     "b200msm_set_profiling": (ctypes.c_int, [ctypes.c_int]),
     "b200msm_last_phase_ms": (ctypes.c_int, [f64p]),

@@ -29,7 +29,7 @@ template <class F>
 __global__ void __launch_bounds__(128)
 k_accumulate(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ vals,
              const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, uint32_t nb,
-             uint32_t heavy_thr, uint32_t *__restrict__ buckets) {
+             uint32_t heavy_thr, const uint32_t *__restrict__ endo_x, uint32_t n_pts, uint32_t *__restrict__ buckets) {
     constexpr int W = field_words<F>::value;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nb) return;
@@ -40,14 +40,22 @@ k_accumulate(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ va
     xyzz_set_inf(acc);
     uint32_t v = s < e ? vals[s] : 0;
     for (uint32_t j = s; j < e; j++) {
-        const uint32_t *p = bases + (size_t)(v & 0x7fffffffu) * (2 * W);
+        // index ≥ n_pts (GLV): the endomorphism image φ(P) = (β·x, y) of point index − n_pts, whose
+        // x comes from the precomputed β·x table
+        uint32_t idx = v & 0x7fffffffu;
+        const bool endo = idx >= n_pts;
+        if (endo) idx -= n_pts;
+        const uint32_t *p = bases + (size_t)idx * (2 * W);
+        const uint32_t *px = endo ? endo_x + (size_t)idx * W : p;
         const uint32_t sign = v >> 31;
         F x, y;
-        f_load(x, p);
+        f_load(x, px);
         f_load(y, p + W);
         if (j + 1 < e) {  // pull the next point towards L1 while this one is being added
             v = vals[j + 1];
-            const char *q = reinterpret_cast<const char *>(bases + (size_t)(v & 0x7fffffffu) * (2 * W));
+            uint32_t nidx = v & 0x7fffffffu;
+            if (nidx >= n_pts) nidx -= n_pts;
+            const char *q = reinterpret_cast<const char *>(bases + (size_t)nidx * (2 * W));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(q + 8 * W - 4));
         }
@@ -56,6 +64,20 @@ k_accumulate(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ va
         xyzz_madd(acc, x, y);
     }
     xyzz_store(buckets + (size_t)b * (4 * W), acc);
+}
+
+// β·x for every base (G1 GLV): one product per point, written as a dense n×48-byte table
+__device__ __constant__ const uint32_t GLV_BETA[12] = {0x8671f071, 0xcd03c9e4, 0x1fcda5d2, 0x5dab2246, 0xd3851b95, 0x587042af,
+                                                       0x01bacb9e, 0x8eb60ebe, 0x83d050d2, 0x03f97d6e, 0x54638741, 0x18f02065};
+static __global__ void __launch_bounds__(256)
+k_endo_table(const uint32_t *__restrict__ bases, size_t n, uint32_t *__restrict__ endo_x) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp x, beta;
+    fp_load(x, bases + i * 24);
+    fp_load(beta, GLV_BETA);
+    fp_mul(x, x, beta);
+    fp_store(endo_x + i * 12, x);
 }
 
 // ---- heavy buckets ---------------------------------------------------------------------------
@@ -98,7 +120,8 @@ __device__ __forceinline__ void block_tree_sum(xyzz<F> &acc, uint32_t *smem) {
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_heavy_tasks(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ vals,
-              const HeavyHeader *__restrict__ hdr, const HeavyTask *__restrict__ tasks, uint32_t *__restrict__ partials) {
+              const HeavyHeader *__restrict__ hdr, const HeavyTask *__restrict__ tasks, const uint32_t *__restrict__ endo_x,
+              uint32_t n_pts, uint32_t *__restrict__ partials) {
     constexpr int W = field_words<F>::value;
     constexpr int PW = 4 * W;
     __shared__ __align__(16) uint32_t smem[(THREADS / 2) * PW];
@@ -109,9 +132,12 @@ k_heavy_tasks(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ v
         xyzz_set_inf(acc);
         for (uint32_t j = threadIdx.x; j < tk.len; j += THREADS) {
             uint32_t v = vals[tk.offset + j];
-            const uint32_t *p = bases + (size_t)(v & 0x7fffffffu) * (2 * W);
+            uint32_t idx = v & 0x7fffffffu;
+            const bool endo = idx >= n_pts;
+            if (endo) idx -= n_pts;
+            const uint32_t *p = bases + (size_t)idx * (2 * W);
             F x, y;
-            f_load(x, p);
+            f_load(x, endo ? endo_x + (size_t)idx * W : p);
             f_load(y, p + W);
             if (f_is_zero(x) && f_is_zero(y)) continue;
             f_cneg(y, y, v >> 31);

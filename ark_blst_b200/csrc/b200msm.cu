@@ -67,21 +67,45 @@ struct DevBuf {
 
 struct Plan {
     int c = 0, nwin = 0;
+    bool glv = false;          // G1: split every scalar into two 128-bit halves (k1 + k2·λ)
     uint32_t nbw = 0, nb = 0;  // buckets per window, total
 };
 
-// SURVEY §8(d) work model, minimised over c; the same expression the roofline numerator uses.
-int auto_window(size_t n, bool g2) {
-    double madd = g2 ? 28 : 10, add = g2 ? 40 : 14, dbl = g2 ? 25 : 9;
+// Window width and GLV choice from a time model fitted to the measured phases on B200 (µs):
+// accumulation at 88 % (G1) / 76 % (G2) of the 18.5 T IMAD/s pipe, the fan-in-32 reduction level
+// at 55 %, 3.4 µs (G1) / 11 µs (G2) per dependent doubling of the Horner chain, 23 ps per sorted
+// entry.  Without GLV this lands on the work-minimising c* of SURVEY §8(d) (13/16/18/20 at
+// 2^16/20/22/24) — the width the roofline numerator assumes.
+double plan_time_us(size_t n, bool g2, bool glv, int c) {
+    const double bits = glv ? 129 : 256, W = std::ceil(bits / c), entries = (glv ? 2.0 : 1.0) * (double)n;
+    const double madd = g2 ? 28 : 10, add = g2 ? 40 : 14, pipe = 18.5e6;  // IMAD per µs
+    double t = entries * W * madd * 588 / (pipe * (g2 ? 0.76 : 0.88));
+    t += W * std::pow(2.0, c - 1) * 2 * add * 588 / (pipe * 0.55);
+    t += W * c * (g2 ? 11.0 : 3.4) + 250;
+    t += entries * W * 2.3e-5;
+    if (glv) t += (double)n * 588 / (pipe * 0.5);
+    return t;
+}
+void auto_plan(size_t n, bool g2, int glv_mode, int c_override, Plan &pl) {
     double best = 1e300;
-    int bc = 2;
-    for (int c = 2; c <= 22; c++) {
-        double W = std::ceil(256.0 / c);
-        double cost = (double)n * W * (1.0 - std::pow(2.0, -c)) * madd + W * std::pow(2.0, c - 1) * 2 * add +
-                      W * (c * dbl + add);
-        if (cost < best) { best = cost; bc = c; }
+    for (int glv = 0; glv <= (g2 ? 0 : 1); glv++) {
+        if (glv_mode == 0 && glv) continue;
+        if (glv_mode == 1 && !glv && !g2) continue;
+        if (glv && 2 * n >= (1ull << 31)) continue;
+        for (int c = 2; c <= 22; c++) {
+            if (c_override > 0 && c != c_override) continue;
+            double t = plan_time_us(n, g2, glv, c);
+            if (t < best) { best = t; pl.c = c; pl.glv = glv; }
+        }
     }
-    return bc;
+    pl.nwin = ((pl.glv ? 129 : 256) + pl.c - 1) / pl.c;  // c·W ≥ bits + 1: the top Booth carry stays inside
+    pl.nbw = 1u << (pl.c - 1);
+    pl.nb = pl.nbw * (uint32_t)pl.nwin;
+}
+int auto_window(size_t n, bool g2) {  // non-GLV width (scratch estimates)
+    Plan pl;
+    auto_plan(n, g2, 0, 0, pl);
+    return pl.c;
 }
 
 struct DeviceCtx {
@@ -92,7 +116,7 @@ struct DeviceCtx {
     bool busy_valid = false;
     size_t fits_n[2] = {0, 0};  // largest n per group that already ran as a single pass (arena is big enough)
     DevBuf bases, scalars, digits, vals, start, cnt, ord, buckets, lvlR[2], lvlC[2], out;
-    DevBuf hvy_hdr, hvy_buckets, hvy_tasks, hvy_partials, treeS[2], treeV[2], treeC[2], wsum, chunk_partials, norm_in, norm_out, tile_sums, size_hist;
+    DevBuf hvy_hdr, hvy_buckets, hvy_tasks, hvy_partials, treeS[2], treeV[2], treeC[2], wsum, chunk_partials, norm_in, norm_out, tile_sums, size_hist, endo;
     cudaEvent_t ev[8] = {};
     double phase_ms[8] = {};
     bool phase_pending = false;
@@ -109,7 +133,7 @@ struct DeviceCtx {
     }
     void release_all() {
         for (DevBuf *b : {&bases, &scalars, &digits, &vals, &start, &cnt, &ord, &buckets, &lvlR[0], &lvlR[1], &lvlC[0], &lvlC[1], &out, &hvy_hdr, &hvy_buckets,
-                          &hvy_tasks, &hvy_partials, &treeS[0], &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum, &chunk_partials, &norm_in, &norm_out, &tile_sums, &size_hist})
+                          &hvy_tasks, &hvy_partials, &treeS[0], &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum, &chunk_partials, &norm_in, &norm_out, &tile_sums, &size_hist, &endo})
             b->release();
     }
 };
@@ -120,6 +144,7 @@ struct Engine {
     std::vector<std::unique_ptr<DeviceCtx>> ctx;
     int window_override = 0;
     size_t max_chunk_override = 0;
+    int glv_mode = 0;   // -1 automatic (time model), 0 never (default: measured slower, see profiles/r01_experiments.md), 1 always (G1 only)
     bool profiling = false;
 };
 Engine g_eng;
@@ -189,12 +214,9 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
         return 0;
     }
     Plan pl;
-    pl.c = g_eng.window_override > 0 ? g_eng.window_override : auto_window(n, g2);
-    pl.c = std::max(2, std::min(pl.c, 24));
-    pl.nwin = (256 + pl.c - 1) / pl.c;  // c·W ≥ 256 > 255 = |r|: the top Booth carry stays inside
-    pl.nbw = 1u << (pl.c - 1);
-    pl.nb = pl.nbw * (uint32_t)pl.nwin;
-    const size_t m = n * (size_t)pl.nwin;
+    auto_plan(n, g2, g_eng.glv_mode, std::min(g_eng.window_override, 22), pl);
+    const size_t entries = pl.glv ? 2 * n : n;  // per window
+    const size_t m = entries * (size_t)pl.nwin;
     const bool prof = g_eng.profiling;
     int evi = 0;
     auto mark = [&]() { if (prof) cudaEventRecord(cx.ev[evi++], st); };
@@ -216,7 +238,7 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     // ≈ m/175k bucket-entry times — or when it exceeds 3× the mean occupancy, whichever is larger.
     // Buckets are taken in decreasing-size order, so the long chains start first.
     // Worst-case list sizes follow from Σ counts = m.
-    const uint32_t avg = (uint32_t)((n + pl.nbw - 1) / pl.nbw);
+    const uint32_t avg = (uint32_t)((entries + pl.nbw - 1) / pl.nbw);
     const uint32_t heavy_thr = std::max<uint32_t>(std::max<uint32_t>(32, 3 * avg), (uint32_t)(m / 175000));
     const size_t max_heavy = m / (heavy_thr + 1) + 1, max_tasks = m / HEAVY_CHUNK + max_heavy + 1;
     if (int rc = cx.hvy_hdr.reserve(16)) return rc;
@@ -231,7 +253,7 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     mark();
     // 1+2. canonical scalars → window digits, per-bucket histogram, scan → bucket offsets, scatter
     //      of the point indices (a counting sort on the bucket id; zero digits are dropped)
-    launch_group_by_bucket(d_scalars, n, mont, pl.c, pl.nwin, pl.nb, cx.digits.as<uint32_t>(), cx.cnt.as<uint32_t>(), start,
+    launch_group_by_bucket(d_scalars, n, mont, pl.glv ? 1 : 0, pl.c, pl.nwin, pl.nb, cx.digits.as<uint32_t>(), cx.cnt.as<uint32_t>(), start,
                            cx.tile_sums.as<uint32_t>(), vals, st);
     mark();
     mark();
@@ -241,15 +263,23 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     // 4. bucket accumulation
     CUDA_TRY(cudaMemsetAsync(cx.hvy_hdr.p, 0, 16, st));
     if (bases_ready) CUDA_TRY(cudaStreamWaitEvent(st, bases_ready, 0));
+    const uint32_t *endo_x = nullptr;
+    uint32_t n_pts = 0xffffffffu;
+    if (pl.glv) {  // β·x table for the endomorphism images (one product per base)
+        if (int rc = cx.endo.reserve(n * 48)) return rc;
+        launch_endo_table_g1(d_bases, n, cx.endo.as<uint32_t>(), st);
+        endo_x = cx.endo.as<uint32_t>();
+        n_pts = (uint32_t)n;
+    }
     // heavy buckets run on a side stream next to the light kernel (disjoint outputs): each fills
     // the SMs the other leaves idle at its tail
     CUDA_TRY(cudaEventRecord(cx.ev_fork, st));
     CUDA_TRY(cudaStreamWaitEvent(cx.aux_stream, cx.ev_fork, 0));
-    (g2 ? launch_heavy_g2 : launch_heavy_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, cx.hvy_hdr.p,
+    (g2 ? launch_heavy_g2 : launch_heavy_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, endo_x, n_pts, cx.hvy_hdr.p,
                                              cx.hvy_buckets.p, cx.hvy_tasks.p, cx.hvy_partials.as<uint32_t>(),
                                              cx.buckets.as<uint32_t>(), cx.sm_count * 4, cx.aux_stream);
     CUDA_TRY(cudaEventRecord(cx.ev_join, cx.aux_stream));
-    (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr,
+    (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, endo_x, n_pts,
                                                        cx.buckets.as<uint32_t>(), st);
     CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_join, 0));
     mark();
@@ -304,9 +334,9 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
 size_t pass_scratch_bytes(size_t n, bool g2, int c_override) {
     int c = c_override > 0 ? c_override : auto_window(n, g2);
     c = std::max(2, std::min(c, 24));
-    size_t nwin = (256 + c - 1) / c, nb = nwin << (c - 1), m = n * nwin;
+    size_t nwin = (256 + c - 1) / c, nb = nwin << (c - 1), m = n * nwin;  // the GLV plan needs about the same
     size_t PB = g2 ? 384 : 192;
-    return m * 8 + nb * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + (64u << 20);
+    return m * 8 + nb * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + n * 48 + (64u << 20);
 }
 
 // The whole MSM on one device: one pass when it fits, otherwise the chunking the reference left
@@ -330,9 +360,10 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases, const void *d_scala
     size_t chunks = 1;
     auto too_big = [&](size_t cn) {
         if (g_eng.max_chunk_override) return cn > g_eng.max_chunk_override;
-        int c = g_eng.window_override > 0 ? g_eng.window_override : auto_window(cn, g2);
-        size_t nwin = (256 + c - 1) / c;
-        return cn * nwin >= 0xfff00000ull || cn >= (1ull << 31) || pass_scratch_bytes(cn, g2, g_eng.window_override) > budget;
+        Plan p;
+        auto_plan(cn, g2, g_eng.glv_mode, std::min(g_eng.window_override, 22), p);
+        size_t ent = (p.glv ? 2 : 1) * cn;
+        return ent * p.nwin >= 0xfff00000ull || cn >= (1ull << 30) || pass_scratch_bytes(cn, g2, g_eng.window_override) > budget;
     };
     while (too_big((n + chunks - 1) / chunks)) {
         chunks *= 2;
@@ -610,6 +641,11 @@ int b200msm_normalize_batch(int group, const uint64_t *proj, size_t n, uint64_t 
 int b200msm_set_window_bits(int c) {
     if (c < 0 || c == 1 || c > 24) return fail(B200MSM_EINVAL, "window bits must be 0 (auto) or 2..24");
     g_eng.window_override = c;
+    return 0;
+}
+int b200msm_set_glv(int mode) {
+    if (mode < -1 || mode > 1) return fail(B200MSM_EINVAL, "glv mode must be -1 (auto), 0 (off) or 1 (on)");
+    g_eng.glv_mode = mode;
     return 0;
 }
 int b200msm_set_max_chunk(size_t max_points_per_pass) {

@@ -23,20 +23,32 @@ __global__ void k_digits_dbg(const uint32_t *__restrict__ scalars, size_t n, int
 // digit), exclusive scan, (2) scatter point indices to start[b] + cursor[b]++, window by window.
 // Zero digits are dropped instead of being carried to a sentinel bucket, and the scan directly
 // yields the bucket offsets.
+// `glv` (G1 only): every scalar is split into (k1, k2) with k = k1 + k2·λ; entry i of a window is
+// k1's digit for point i, entry n + i is k2's digit for the endomorphism image φ(P_i).
 __global__ void __launch_bounds__(256)
-k_hist(const uint32_t *__restrict__ scalars, size_t n, int mont, int c, int nwin, uint32_t *__restrict__ dig,
+k_hist(const uint32_t *__restrict__ scalars, size_t n, int mont, int glv, int c, int nwin, uint32_t *__restrict__ dig,
        uint32_t *__restrict__ count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t s[8];
+    uint32_t s[8], s2[8];
     load_scalar(s, scalars, i, mont);
+    if (glv) {
+        uint32_t k[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) k[j] = s[j];
+        glv_decompose(k, s, s2);
+    }
     const uint32_t nbw = 1u << (c - 1);
-    for (int w = 0; w < nwin; w++) {
-        int d = booth_digit(s, w, c);
-        uint32_t neg = d < 0;
-        uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
-        dig[(size_t)w * n + i] = (mag << 1) | neg;   // window-major: coalesced; 0 = zero digit
-        if (mag) atomicAdd(&count[(uint32_t)w * nbw + (mag - 1)], 1u);
+    const size_t per_window = glv ? 2 * n : n;
+    for (int half = 0; half <= glv; half++) {
+        const uint32_t *sc = half ? s2 : s;
+        for (int w = 0; w < nwin; w++) {
+            int d = booth_digit(sc, w, c);
+            uint32_t neg = d < 0;
+            uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
+            dig[(size_t)w * per_window + (half ? n : 0) + i] = (mag << 1) | neg;   // window-major; 0 = zero digit
+            if (mag) atomicAdd(&count[(uint32_t)w * nbw + (mag - 1)], 1u);
+        }
     }
 }
 // grid (point blocks, windows): blocks are dispatched window after window, so at any time the
@@ -180,17 +192,18 @@ k_size_scatter(const uint32_t *__restrict__ start, uint32_t nb, uint32_t *__rest
         if (bin[k] != 0xffffffffu) order[lh[bin[k]] + rank[k]] = b0 + k;
 }
 
-void launch_group_by_bucket(const uint32_t *scalars, size_t n, int mont, int c, int nwin, uint32_t nb, uint32_t *dig,
+void launch_group_by_bucket(const uint32_t *scalars, size_t n, int mont, int glv, int c, int nwin, uint32_t nb, uint32_t *dig,
                             uint32_t *count, uint32_t *start, uint32_t *tile_sums, uint32_t *vals, cudaStream_t st) {
     for (int k = 0; k < 7; k++) count_launch();
     cudaMemsetAsync(count, 0, (size_t)nb * 4, st);
-    k_hist<<<blocks_for(n, 256), 256, 0, st>>>(scalars, n, mont, c, nwin, dig, count);
+    k_hist<<<blocks_for(n, 256), 256, 0, st>>>(scalars, n, mont, glv, c, nwin, dig, count);
     size_t ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
     k_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(count, start, nb, tile_sums);
     k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, ntiles, tile_sums + ntiles);
     k_scan_add<<<blocks_for(nb, 256), 256, 0, st>>>(start, nb, tile_sums, tile_sums + ntiles);
     cudaMemsetAsync(count, 0, (size_t)nb * 4, st);   // reused as the scatter cursors
-    k_scatter<<<dim3(blocks_for(n, 256), (unsigned)nwin), 256, 0, st>>>(dig, n, c, start, count, vals);
+    const size_t entries = glv ? 2 * n : n;  // per window
+    k_scatter<<<dim3(blocks_for(entries, 256), (unsigned)nwin), 256, 0, st>>>(dig, entries, c, start, count, vals);
 }
 // hist: 2·SIZE_BINS u32 of scratch
 void launch_order_by_size(const uint32_t *start, uint32_t nb, uint32_t *hist, uint32_t *order, cudaStream_t st) {

@@ -11,24 +11,27 @@ namespace b200msm {
 // k_prep.cu
 void launch_digits_dbg(const uint32_t *scalars, size_t n, int mont, int c, int nwin, int *out, cudaStream_t st);
 // hand-written grouping by bucket (counting sort on the bucket id, built from the scalars):
-// dig: n·nwin u32, count: nb u32, start: nb+2 u32, tile_sums: nb/2048+2 u32, vals: ≥ n·nwin u32
-void launch_group_by_bucket(const uint32_t *scalars, size_t n, int mont, int c, int nwin, uint32_t nb, uint32_t *dig,
+// glv: split every scalar in two 128-bit halves (entries per window double); dig: entries·nwin u32, count: nb u32, start: nb+2 u32, tile_sums: nb/2048+2 u32, vals: ≥ n·nwin u32
+void launch_group_by_bucket(const uint32_t *scalars, size_t n, int mont, int glv, int c, int nwin, uint32_t nb, uint32_t *dig,
                             uint32_t *count, uint32_t *start, uint32_t *tile_sums, uint32_t *vals, cudaStream_t st);
 // bucket ids in decreasing-size order (counting sort on the clamped size); hist: 8192 u32 scratch
 void launch_order_by_size(const uint32_t *start, uint32_t nb, uint32_t *hist, uint32_t *order, cudaStream_t st);
 // k_accumulate_g{1,2}.cu
 constexpr uint32_t HEAVY_CHUNK = 4096;  // entries per block task of a heavy bucket
+// endo_x / n_pts: GLV (G1): value indices ≥ n_pts name φ(P) = (β·x, y) of point index − n_pts, x read from
+// the β·x table; pass nullptr / 0xffffffff when unused
 void launch_accumulate_g1(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
-                          uint32_t nb, uint32_t heavy_thr, uint32_t *buckets, cudaStream_t st);
+                          uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, uint32_t *buckets, cudaStream_t st);
 void launch_accumulate_g2(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
-                          uint32_t nb, uint32_t heavy_thr, uint32_t *buckets, cudaStream_t st);
+                          uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, uint32_t *buckets, cudaStream_t st);
+void launch_endo_table_g1(const uint32_t *bases, size_t n, uint32_t *endo_x, cudaStream_t st);
 // plan + block tasks + per-bucket fold for buckets above heavy_thr; hdr must be zeroed (8 bytes)
 void launch_heavy_g1(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
-                     uint32_t nb, uint32_t heavy_thr, void *hdr, void *hb, void *tasks, uint32_t *partials,
-                     uint32_t *buckets, int grid, cudaStream_t st);
+                     uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, void *hdr, void *hb, void *tasks,
+                     uint32_t *partials, uint32_t *buckets, int grid, cudaStream_t st);
 void launch_heavy_g2(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
-                     uint32_t nb, uint32_t heavy_thr, void *hdr, void *hb, void *tasks, uint32_t *partials,
-                     uint32_t *buckets, int grid, cudaStream_t st);
+                     uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, void *hdr, void *hb, void *tasks,
+                     uint32_t *partials, uint32_t *buckets, int grid, cudaStream_t st);
 
 // k_reduce_g{1,2}.cu
 void launch_wsum_level_g1(const uint32_t *X, const uint32_t *Cin, uint32_t len, uint32_t m, int log2M, uint32_t nwin,

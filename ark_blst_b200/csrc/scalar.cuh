@@ -70,4 +70,87 @@ __device__ __forceinline__ void load_scalar(uint32_t *s, const uint32_t *scalars
     else { if (fr_geq_r(s)) fr_sub_r(s); if (fr_geq_r(s)) fr_sub_r(s); }  // 2^256 < 3r
 }
 
+// ---- GLV decomposition for G1 -------------------------------------------------------------------
+// BLS12-381 has r = λ² + λ + 1 with λ = z² − 1 (128 bits) and the endomorphism φ(x, y) = (βx, y) = λ·(x, y)
+// on G1.  For a canonical k < r:  k = k1 + k2·λ with k2 = ⌊k/λ⌋ ≤ λ + 1 and k1 = k mod λ — both
+// non-negative and below 2^128 — so k·P = k1·P + k2·φ(P): twice the points, half the scalar bits,
+// i.e. half the windows for the Horner chain (the MSM's serial tail).  ⌊k/λ⌋ by Barrett with
+// μ = ⌊2^256/λ⌋ (at most one correction step; checked against big-int arithmetic in the tests).
+__device__ __constant__ const uint32_t GLV_LAMBDA[4] = {0xffffffff, 0x00000000, 0x0001a402, 0xac45a401};
+__device__ __constant__ const uint32_t GLV_MU[5] = {0xf6cfee30, 0x63f6e522, 0xe01faadd, 0x7c6becf1, 0x00000001};
+
+__device__ __forceinline__ void glv_decompose(const uint32_t *k, uint32_t *k1, uint32_t *k2) {
+    // q = (k·μ) >> 256 : 8×5 limbs, only limbs 8..12 of the product are kept
+    uint32_t prod[13];
+#pragma unroll
+    for (int i = 0; i < 13; i++) prod[i] = 0;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            c += (uint64_t)k[i] * GLV_MU[j] + prod[i + j];
+            prod[i + j] = (uint32_t)c;
+            c >>= 32;
+        }
+        prod[8 + j] = (uint32_t)c;
+    }
+    uint32_t q[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) q[i] = prod[8 + i];
+    // r = k − q·λ on 5 limbs (the true remainder is < 3λ < 2^130)
+    uint32_t ql[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) ql[i] = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = 0; i + j < 5; i++) {
+            c += (uint64_t)q[i] * GLV_LAMBDA[j] + ql[i + j];
+            ql[i + j] = (uint32_t)c;
+            c >>= 32;
+        }
+    }
+    uint32_t r[5];
+    uint64_t brw = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        uint64_t d = (uint64_t)k[i] - ql[i] - brw;
+        r[i] = (uint32_t)d;
+        brw = (d >> 32) & 1;
+    }
+    for (int it = 0; it < 3; it++) {                   // r ≥ λ → r −= λ, q += 1 (≤ 2 times)
+        bool ge = r[4] != 0;
+        if (!ge) {
+            ge = true;
+#pragma unroll
+            for (int i = 3; i >= 0; i--) {
+                if (r[i] > GLV_LAMBDA[i]) break;
+                if (r[i] < GLV_LAMBDA[i]) { ge = false; break; }
+            }
+        }
+        if (!ge) break;
+        brw = 0;
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            uint64_t d = (uint64_t)r[i] - (i < 4 ? GLV_LAMBDA[i] : 0u) - brw;
+            r[i] = (uint32_t)d;
+            brw = (d >> 32) & 1;
+        }
+        uint64_t c = 1;
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            c += q[i];
+            q[i] = (uint32_t)c;
+            c >>= 32;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        k1[i] = i < 4 ? r[i] : 0;
+        k2[i] = i < 4 ? q[i] : 0;
+    }
+}
+
 }  // namespace b200msm

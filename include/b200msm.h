@@ -99,6 +99,9 @@ unsigned long long b200msm_launch_count(void);
 
 /* Tunables (SURVEY §5 "config/flags"): window width c; 0 = automatic from n. */
 int b200msm_set_window_bits(int c);
+/* G1 only: GLV split of every scalar into two 128-bit halves over (P, φ(P)) — halves the windows
+ * of the on-device Horner chain. -1 = automatic (time model), 0 = never, 1 = always. */
+int b200msm_set_glv(int mode);
 /* Large inputs are cut into passes automatically (sort arrays < 2^32 entries, scratch within the
  * free HBM) — the chunking the reference left as a TODO (src/gpu.rs:238-239). A non-zero value
  * forces at most that many points per pass (tests); 0 = automatic. */

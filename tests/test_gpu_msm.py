@@ -182,3 +182,27 @@ def test_chunked_passes(eng, cref, g2):
         finally:
             L.b200msm_set_max_chunk(0)
         assert cref.affine_equal(g2, got, exp), chunk
+
+
+@pytest.mark.parametrize("n", [1, 9, 700, 20000])
+def test_glv_path(eng, cref, n):
+    """G1 GLV split (k = k1 + k2·λ over P and φ(P)) — off by default, forced on here — must give
+    the same group element; includes scalars around λ and identity bases"""
+    bases = cref.synth_bases(0, 71 + n, n)
+    sc_int = [o.limbs_to_int(r) for r in cref.synth_scalars(72 + n, n, False).tolist()]
+    lam = o.BLS_X * o.BLS_X - 1
+    for k, v in enumerate([0, 1, lam - 1, lam, lam + 1, o.R_ORDER - 1, lam * lam, (1 << 128) - 1, 1 << 128]):
+        if k < n:
+            sc_int[k] = v % o.R_ORDER
+    if n > 12:
+        bases[11] = 0
+    sc = scalars_to_limbs(sc_int, False)
+    exp = cref.msm(0, bases, sc, 0)
+    L = eng._lib.lib
+    assert L.b200msm_set_glv(1) == 0
+    try:
+        got = eng.G1Projective.msm_bigint(bases, sc)
+        got_m = eng.G1Projective.msm(bases, scalars_to_limbs(sc_int, True))
+    finally:
+        L.b200msm_set_glv(0)
+    assert cref.affine_equal(0, got, exp) and cref.affine_equal(0, got_m, exp)
