@@ -141,7 +141,7 @@ k_heavy_tasks(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ v
             f_load(y, p + W);
             if (f_is_zero(x) && f_is_zero(y)) continue;
             f_cneg(y, y, v >> 31);
-            xyzz_madd_ni(acc, x, y);
+            xyzz_madd(acc, x, y);                      // inlined: the accumulator stays in registers
         }
         block_tree_sum<F, THREADS>(acc, smem);
         if (threadIdx.x == 0) xyzz_store(partials + (size_t)t * PW, acc);
