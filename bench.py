@@ -369,6 +369,95 @@ def run_ours(args):
     return 0
 
 
+def run_groth16(args):
+    """BASELINE.json configs[4]: a Groth16-prover-shaped batch — three G1 MSMs and one G2 MSM of
+    2^logn points each, issued back to back, every MSM sharded over the ranks (non-default mode:
+    `--workload groth16`, default logn 22). Device-resident inputs; one JSON line from rank 0."""
+    import numpy as np
+    import torch
+
+    import ark_blst_b200 as eng
+    from oracle import cref
+
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    L = eng._lib.lib
+    eng._lib.check(L.b200msm_init(local, 1), "init")
+    n_total = 1 << args.logn
+    lo, hi = n_total * rank // world, n_total * (rank + 1) // world
+    n = hi - lo
+    stream = torch.cuda.current_stream().cuda_stream
+    jobs = []  # (group, bases, scalars, seeds)
+    for k, g2 in enumerate((0, 0, 0, 1)):
+        aw = 24 if g2 else 12
+        sb, ss = SEED_BASES + 7919 * k + 1000003 * rank, SEED_SCALARS + 7919 * k + 1000003 * rank
+        b = torch.empty((n, aw), dtype=torch.int64, device=dev)
+        s = torch.empty((n, 4), dtype=torch.int64, device=dev)
+        eng.synth_bases_device(g2, sb, n, b.data_ptr(), stream)
+        eng.synth_scalars_device(ss, n, True, s.data_ptr(), stream)
+        jobs.append((g2, b, s, sb, ss, torch.zeros(36 if g2 else 18, dtype=torch.int64, device=dev)))
+    torch.cuda.synchronize()
+    peak = eng.imad_peak()["imad_per_s"] if rank == 0 else None
+
+    def step():
+        outs = []
+        for g2, b, s, _, _, part in jobs:
+            eng.run_device(g2, b.data_ptr(), s.data_ptr(), n, True, part.data_ptr(), stream)
+            if world > 1:
+                gathered = torch.empty((world, part.numel()), dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(gathered.view(-1), part)
+                if rank == 0:
+                    res = torch.zeros_like(part)
+                    eng.sum_partials_device(g2, gathered.data_ptr(), world, res.data_ptr(), stream)
+                    outs.append(res)
+            else:
+                outs.append(part)
+        return outs
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        outs = step()
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ok = True
+    for g2, b, s, sb, ss, part in jobs:   # every rank checks its own partial against the dlog closed form
+        exp = cref.msm_by_dlog(g2, sb, cref.synth_scalars(ss, n, False))
+        ok = ok and cref.affine_equal(g2, part.cpu().numpy().view(np.uint64), exp)
+    okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        imad = (3 * work_model(n_total, False)[2] + work_model(n_total, True)[2]) * FPMUL_IMAD
+        print(json.dumps({
+            "metric": "Groth16-shaped batch: 3xG1 + 1xG2 MSM, ms per batch", "value": ms, "unit": "ms", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32x12 Montgomery limbs (integer)", "data": "synthetic",
+            "config": {"workload": f"3xG1 + 1xG2 MSM at 2^{args.logn} points each, sharded over {world} GPU(s), uniform scalars"},
+            "parity_ok": bool(okt.item()),
+            "roofline": {"bound": "imad", "achieved": imad / (ms * 1e-3) / 1e12, "peak": peak * world / 1e12, "unit": "TIMAD/s",
+                         "frac": imad / (ms * 1e-3) / (peak * world), "traffic": None, "algorithmic_imad": imad}}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def _measured_hbm():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -383,12 +472,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--group", default="g1", choices=["g1", "g2"])
-    ap.add_argument("--logn", type=int, default=20, help="log2 of points per GPU")
+    ap.add_argument("--logn", type=int, default=None, help="log2 of points per GPU (default 20; groth16 workload: total points, default 22)")
+    ap.add_argument("--workload", default="msm", choices=["msm", "groth16"])
     ap.add_argument("--ref-sample-logn", type=int, default=20, help="reference arm: points actually timed per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    if args.logn is None:
+        args.logn = 22 if args.workload == "groth16" else 20
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    if args.workload == "groth16" and args.impl == "b200":
+        return run_groth16(args)
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 
 
