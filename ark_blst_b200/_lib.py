@@ -32,6 +32,8 @@ SIGNATURES = {
     "b200msm_sum_partials_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int, vp, vp]),
     "b200msm_normalize_batch": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_size_t, u64p]),
     "b200msm_normalize_batch_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, vp, vp]),
+    "b200msm_deserialize": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_uint8), ctypes.c_size_t, ctypes.c_int, ctypes.c_int, u64p, ctypes.POINTER(ctypes.c_uint8)]),
+    "b200msm_serialize": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_uint8)]),
     "b200msm_launch_count": (ctypes.c_ulonglong, []),
     "b200msm_set_window_bits": (ctypes.c_int, [ctypes.c_int]),
     "b200msm_set_glv": (ctypes.c_int, [ctypes.c_int]),

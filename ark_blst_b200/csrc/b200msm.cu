@@ -638,6 +638,54 @@ int b200msm_normalize_batch(int group, const uint64_t *proj, size_t n, uint64_t 
     return rc;
 }
 
+int b200msm_deserialize(int group, const uint8_t *in, size_t n, int compressed, int validate, uint64_t *affine_out,
+                        uint8_t *status_out) {
+    if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "bad group");
+    if (n == 0) return 0;
+    if (!in || !affine_out || !status_out) return fail(B200MSM_EINVAL, "null pointer");
+    if (int rc = engine_init(-1, 1)) return rc;
+    DeviceCtx &cx = *g_eng.ctx[0];
+    std::lock_guard<std::mutex> lk(cx.mu);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(cx.dev);
+    const size_t AB = aff_bytes(group), EB = compressed ? AB / 2 : AB;
+    int rc = 0;
+    if (!(rc = cx.norm_in.reserve(n * EB + n)) && !(rc = cx.norm_out.reserve(n * AB))) {
+        uint8_t *d_in = cx.norm_in.as<uint8_t>(), *d_st = d_in + n * EB;
+        cudaMemcpyAsync(d_in, in, n * EB, cudaMemcpyHostToDevice, cx.stream);
+        launch_deserialize(group == B200MSM_G2, d_in, n, compressed, validate, cx.norm_out.as<uint32_t>(), d_st, cx.stream);
+        cudaMemcpyAsync(affine_out, cx.norm_out.p, n * AB, cudaMemcpyDeviceToHost, cx.stream);
+        cudaMemcpyAsync(status_out, d_st, n, cudaMemcpyDeviceToHost, cx.stream);
+        cudaError_t e = cudaStreamSynchronize(cx.stream);
+        if (e != cudaSuccess) rc = fail(B200MSM_ECUDA, std::string("deserialize: ") + cudaGetErrorString(e));
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+int b200msm_serialize(int group, const uint64_t *affine, size_t n, int compressed, uint8_t *out) {
+    if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "bad group");
+    if (n == 0) return 0;
+    if (!affine || !out) return fail(B200MSM_EINVAL, "null pointer");
+    if (int rc = engine_init(-1, 1)) return rc;
+    DeviceCtx &cx = *g_eng.ctx[0];
+    std::lock_guard<std::mutex> lk(cx.mu);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(cx.dev);
+    const size_t AB = aff_bytes(group), EB = compressed ? AB / 2 : AB;
+    int rc = 0;
+    if (!(rc = cx.norm_in.reserve(n * AB)) && !(rc = cx.norm_out.reserve(n * EB))) {
+        cudaMemcpyAsync(cx.norm_in.p, affine, n * AB, cudaMemcpyHostToDevice, cx.stream);
+        launch_serialize(group == B200MSM_G2, cx.norm_in.as<uint32_t>(), n, compressed, cx.norm_out.as<uint8_t>(), cx.stream);
+        cudaMemcpyAsync(out, cx.norm_out.p, n * EB, cudaMemcpyDeviceToHost, cx.stream);
+        cudaError_t e = cudaStreamSynchronize(cx.stream);
+        if (e != cudaSuccess) rc = fail(B200MSM_ECUDA, std::string("serialize: ") + cudaGetErrorString(e));
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
 int b200msm_set_window_bits(int c) {
     if (c < 0 || c == 1 || c > 24) return fail(B200MSM_EINVAL, "window bits must be 0 (auto) or 2..24");
     g_eng.window_override = c;

@@ -55,6 +55,11 @@ void launch_sum_partials_g2(const uint32_t *partials, int count, uint32_t *out, 
 // k_normalize.cu
 void launch_normalize_batch(int g2, const uint32_t *proj, size_t n, uint32_t *aff, int sm_count, cudaStream_t st);
 
+// k_serde.cu
+void launch_deserialize(int g2, const uint8_t *in, size_t n, int compressed, int validate, uint32_t *aff, uint8_t *status,
+                        cudaStream_t st);
+void launch_serialize(int g2, const uint32_t *aff, size_t n, int compressed, uint8_t *out, cudaStream_t st);
+
 // k_synth_g{1,2}.cu / k_util.cu
 void launch_synth_bases_g1(uint64_t seed, size_t n, uint32_t *out, cudaStream_t st);
 void launch_synth_bases_g2(uint64_t seed, size_t n, uint32_t *out, cudaStream_t st);

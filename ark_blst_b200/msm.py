@@ -80,6 +80,31 @@ class _Group:
         return out
 
     @classmethod
+    def serialize(cls, affine, compressed=True):
+        """CanonicalSerialize::serialize_{compressed,uncompressed} for a batch of affine points
+        (reference src/g1.rs:358-373) → (n, 48|96|192) uint8"""
+        aff = _u64(affine, cls.AFFINE_WORDS)
+        eb = cls.AFFINE_WORDS * 8 // (2 if compressed else 1)
+        out = np.zeros((aff.shape[0], eb), dtype=np.uint8)
+        u8 = ctypes.POINTER(ctypes.c_uint8)
+        _lib.check(lib.b200msm_serialize(cls.GROUP, _ptr(aff), aff.shape[0], int(compressed), out.ctypes.data_as(u8)), "serialize")
+        return out
+
+    @classmethod
+    def deserialize(cls, data, compressed=True, validate=True):
+        """CanonicalDeserialize::deserialize_with_mode for a batch (reference src/g1.rs:398-431)
+        → (affine (n, 12|24) uint64, status (n,) uint8: 0 ok, 1 malformed, 2 fails Valid::check)"""
+        eb = cls.AFFINE_WORDS * 8 // (2 if compressed else 1)
+        data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1, eb)
+        n = data.shape[0]
+        aff = np.zeros((n, cls.AFFINE_WORDS), dtype=np.uint64)
+        st = np.zeros(n, dtype=np.uint8)
+        u8 = ctypes.POINTER(ctypes.c_uint8)
+        _lib.check(lib.b200msm_deserialize(cls.GROUP, data.ctypes.data_as(u8), n, int(compressed), int(validate), _ptr(aff),
+                                           st.ctypes.data_as(u8)), "deserialize")
+        return aff, st
+
+    @classmethod
     def msm_unchecked(cls, bases, scalars):
         """arkworks' msm_unchecked: truncates to the shorter input instead of erring."""
         bases = _u64(bases, cls.AFFINE_WORDS)

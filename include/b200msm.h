@@ -94,6 +94,18 @@ int b200msm_sum_partials_device(int group, const void *d_partials, int count, vo
 int b200msm_normalize_batch(int group, const uint64_t *proj, size_t n, uint64_t *affine_out);
 int b200msm_normalize_batch_device(int group, const void *d_proj, size_t n, void *d_affine, void *stream);
 
+/* Point (de)serialisation: the ZCash / IETF encodings ↔ affine limbs, replacing the
+ * host-side CanonicalSerialize / CanonicalDeserialize of G1Affine and G2Affine (reference
+ * src/g1.rs:358-431, src/g2.rs:338-411 → blstrs to_/from_compressed, to_/from_uncompressed, and
+ * Valid::check = on curve ∧ torsion free, src/g1.rs:386-396).  Element sizes: G1 48 (compressed) /
+ * 96 bytes, G2 96 / 192 bytes.  status_out[i]: 0 ok; 1 malformed encoding — what blstrs'
+ * from_*_unchecked rejects and the reference unwrap()s (src/g1.rs:411,419); 2 fails Valid::check
+ * (only tested when validate != 0) — the reference's Err(InvalidData).  Entries with status 1 are
+ * written as the identity. */
+int b200msm_deserialize(int group, const uint8_t *in, size_t n, int compressed, int validate,
+                        uint64_t *affine_out, uint8_t *status_out);
+int b200msm_serialize(int group, const uint64_t *affine, size_t n, int compressed, uint8_t *out);
+
 /* Cumulative count of this library's own kernel launches (CUB sort kernels excluded). */
 unsigned long long b200msm_launch_count(void);
 

@@ -365,3 +365,115 @@ def msm_by_dlog(curve, seed_bases, seed_scalars, n, scalars=None):
         s = synth_scalar(seed_scalars, i) if scalars is None else scalars[i]
         acc = (acc + s * synth_dlog(seed_bases, i)) % R_ORDER
     return curve.mul(curve.gen, acc)
+
+
+# ---------------------------------------------------------------------------------------------
+# ZCash / IETF point encodings. Reference: CanonicalSerialize/Deserialize for
+# G1Affine / G2Affine, src/g1.rs:358-431, src/g2.rs:338-411 → blstrs to_compressed /
+# to_uncompressed / from_*_unchecked, then Valid::check (on curve ∧ torsion free, src/g1.rs:386-396).
+# Big-endian coordinates; G2 coordinates are written c1 then c0; three flag bits in byte 0:
+#   0x80 compressed, 0x40 infinity (everything else zero), 0x20 y is the lexicographically
+#   larger of (y, −y) (compressed form only).
+# ---------------------------------------------------------------------------------------------
+def fp_sqrt(a):
+    """p ≡ 3 (mod 4): a^((p+1)/4), or None if a is a non-residue"""
+    r = pow(a, (P + 1) // 4, P)
+    return r if r * r % P == a % P else None
+
+
+def fp2_pow(a, e):
+    F = Fp2Ops
+    r = F.one
+    for bit in bin(e)[2:]:
+        r = F.sqr(r)
+        if bit == "1":
+            r = F.mul(r, a)
+    return r
+
+
+def fp2_sqrt(a):
+    """Adj / Rodríguez-Henríquez Algorithm 9 for p ≡ 3 (mod 4); None if no root"""
+    F = Fp2Ops
+    if F.is_zero(a):
+        return F.zero
+    a1 = fp2_pow(a, (P - 3) // 4)
+    alpha = F.mul(F.sqr(a1), a)
+    a0 = F.mul((alpha[0], (-alpha[1]) % P), alpha)  # α^p · α (Frobenius = conjugation)
+    if F.eq(a0, (P - 1, 0)):
+        return None
+    x0 = F.mul(a1, a)
+    if F.eq(alpha, (P - 1, 0)):
+        x = ((-x0[1]) % P, x0[0])  # u·x0
+    else:
+        b = fp2_pow(F.add(F.one, alpha), (P - 1) // 2)
+        x = F.mul(b, x0)
+    return x if F.eq(F.sqr(x), a) else None
+
+
+def _lex_largest(F, y):
+    half = (P - 1) // 2
+    if F is Fp2Ops:
+        return y[1] > half or (y[1] == 0 and y[0] > half)
+    return y > half
+
+
+def _coord_bytes(F, v):
+    return (v[1].to_bytes(48, "big") + v[0].to_bytes(48, "big")) if F is Fp2Ops else v.to_bytes(48, "big")
+
+
+def _coord_from(F, b):
+    if F is Fp2Ops:
+        c1, c0 = int.from_bytes(b[:48], "big"), int.from_bytes(b[48:96], "big")
+        return None if c1 >= P or c0 >= P else (c0, c1)
+    v = int.from_bytes(b[:48], "big")
+    return None if v >= P else v
+
+
+def serialize_point(curve, pt, compressed):
+    F = curve.F
+    cb = 96 if F is Fp2Ops else 48
+    if pt is None:
+        out = bytearray(cb if compressed else 2 * cb)
+        out[0] = 0xC0 if compressed else 0x40
+        return bytes(out)
+    out = bytearray(_coord_bytes(F, pt[0]) + (b"" if compressed else _coord_bytes(F, pt[1])))
+    if compressed:
+        out[0] |= 0x80 | (0x20 if _lex_largest(F, pt[1]) else 0)
+    return bytes(out)
+
+
+def deserialize_point(curve, data, compressed, validate):
+    """→ (status, point): status 0 ok, 1 malformed (what blstrs from_*_unchecked rejects; the
+    reference unwrap()s it), 2 fails Valid::check (not on curve / not in the r-torsion)."""
+    F = curve.F
+    cb = 96 if F is Fp2Ops else 48
+    data = bytes(data)
+    flags = data[0] & 0xE0
+    body = bytes([data[0] & 0x1F]) + data[1:]
+    if bool(flags & 0x80) != bool(compressed):
+        return 1, None
+    if flags & 0x40:
+        ok = not any(body) and not (flags & 0x20)
+        return (0, None) if ok else (1, None)
+    if not compressed and (flags & 0x20):
+        return 1, None
+    x = _coord_from(F, body[:cb])
+    if x is None:
+        return 1, None
+    if compressed:
+        rhs = F.add(F.mul(F.sqr(x), x), F.b)
+        y = fp2_sqrt(rhs) if F is Fp2Ops else fp_sqrt(rhs)
+        if y is None:
+            return 1, None
+        if _lex_largest(F, y) != bool(flags & 0x20):
+            y = F.neg(y)
+        pt = (x, y)
+    else:
+        y = _coord_from(F, body[cb : 2 * cb])
+        if y is None:
+            return 1, None
+        pt = (x, y)
+    if validate:
+        if not curve.is_on_curve(pt) or curve.mul(pt, R_ORDER) is not None:
+            return 2, pt
+    return 0, pt

@@ -188,3 +188,27 @@ def test_c_identity_and_edge_scalars(cref):
     exp = C.msm_naive(pts, sc)
     got = cref.msm(0, points_to_limbs(C, pts), scalars_to_limbs(sc, True), 1)
     assert C.eq(C.jac_from_limbs(got.tolist()), exp)
+
+
+# ---- §8f-4 encodings: the oracle against published vectors and itself ----
+def test_point_encoding_kats_and_roundtrip():
+    g1 = "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
+    g2 = ("93e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e"
+          "024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8")
+    assert o.serialize_point(o.G1, o.G1_GEN, True).hex() == g1     # published zkcrypto / IETF encodings
+    assert o.serialize_point(o.G2, o.G2_GEN, True).hex() == g2
+    rng = random.Random(77)
+    for C in (o.G1, o.G2):
+        for _ in range(4):
+            P_ = C.mul(C.gen, rng.randrange(1, o.R_ORDER))
+            for comp in (True, False):
+                st, q = o.deserialize_point(C, o.serialize_point(C, P_, comp), comp, True)
+                assert st == 0 and C.eq(q, P_)
+        for comp in (True, False):
+            st, q = o.deserialize_point(C, o.serialize_point(C, None, comp), comp, True)
+            assert st == 0 and q is None
+    # Fp2 square roots: every square has a root, non-squares are rejected
+    for _ in range(20):
+        a = (rng.randrange(o.P), rng.randrange(o.P))
+        s = o.fp2_sqrt(o.Fp2Ops.sqr(a))
+        assert s is not None and o.Fp2Ops.eq(o.Fp2Ops.sqr(s), o.Fp2Ops.sqr(a))
