@@ -13,6 +13,9 @@ from .msm import (  # noqa: F401
     imad_peak,
     last_phase_ms,
     run_device,
+    run_table_device,
+    table_build_device,
+    table_plan,
     sum_partials_device,
     synth_bases_device,
     synth_scalars_device,

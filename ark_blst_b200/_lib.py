@@ -28,6 +28,11 @@ SIGNATURES = {
     "b200msm_bases_upload": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_size_t, ctypes.POINTER(vp)]),
     "b200msm_bases_free": (ctypes.c_int, [vp]),
     "b200msm_run": (ctypes.c_int, [vp, u64p, ctypes.c_size_t, ctypes.c_int, u64p]),
+    "b200msm_bases_precompute": (ctypes.c_int, [vp, ctypes.c_int]),
+    "b200msm_bases_table_info": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_size_t)]),
+    "b200msm_table_plan": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "b200msm_table_build_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, ctypes.c_int, vp, vp]),
+    "b200msm_run_table_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, ctypes.c_int, vp, ctypes.c_size_t, ctypes.c_int, vp, vp]),
     "b200msm_run_device": (ctypes.c_int, [ctypes.c_int, vp, vp, ctypes.c_size_t, ctypes.c_int, vp, vp]),
     "b200msm_sum_partials_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int, vp, vp]),
     "b200msm_normalize_batch": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_size_t, u64p]),

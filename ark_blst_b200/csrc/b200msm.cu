@@ -102,6 +102,26 @@ void auto_plan(size_t n, bool g2, int glv_mode, int c_override, Plan &pl) {
     pl.nbw = 1u << (pl.c - 1);
     pl.nb = pl.nbw * (uint32_t)pl.nwin;
 }
+// Fixed-base window table (table[w][i] = 2^(c·w)·P_i): one bucket set for all windows, no Horner
+// chain, so the width only trades the n·W additions of the accumulation against one window's
+// bucket reduction (+ a log-depth tree) — wider than the plain plan's at every n.
+struct TableRef {
+    const void *p;     // window-major affine table on the device
+    size_t stride;     // points per window
+    int c, nwin;
+};
+int table_plan(size_t n, bool g2) {
+    const double madd = g2 ? 28 : 10, add = g2 ? 40 : 14, pipe = 18.5e6;
+    double best = 1e300;
+    int bc = 10;
+    for (int c = 10; c <= 23; c++) {           // W ≤ 26: the table stays within 26× the bases
+        const double W = std::ceil(256.0 / c);
+        double t = (double)n * W * madd * 588 / (pipe * (g2 ? 0.76 : 0.88)) + std::pow(2.0, c - 1) * 2 * add * 588 / (pipe * 0.55) +
+                   (double)n * W * 2.3e-5 + c * (g2 ? 40.0 : 16.0);
+        if (t < best) { best = t; bc = c; }
+    }
+    return bc;
+}
 int auto_window(size_t n, bool g2) {  // non-GLV width (scratch estimates)
     Plan pl;
     auto_plan(n, g2, 0, 0, pl);
@@ -116,7 +136,7 @@ struct DeviceCtx {
     bool busy_valid = false;
     size_t fits_n[2] = {0, 0};  // largest n per group that already ran as a single pass (arena is big enough)
     DevBuf bases, scalars, digits, vals, start, cnt, ord, buckets, lvlR[2], lvlC[2], out;
-    DevBuf hvy_hdr, hvy_buckets, hvy_tasks, hvy_partials, treeS[2], treeV[2], treeC[2], wsum, chunk_partials, norm_in, norm_out, tile_sums, size_hist, endo;
+    DevBuf hvy_hdr, hvy_buckets, hvy_tasks, hvy_partials, treeS[2], treeV[2], treeC[2], wsum, chunk_partials, norm_in, norm_out, tile_sums, size_hist, endo, tbl_tmp;
     cudaEvent_t ev[8] = {};
     double phase_ms[8] = {};
     bool phase_pending = false;
@@ -133,7 +153,7 @@ struct DeviceCtx {
     }
     void release_all() {
         for (DevBuf *b : {&bases, &scalars, &digits, &vals, &start, &cnt, &ord, &buckets, &lvlR[0], &lvlR[1], &lvlC[0], &lvlC[1], &out, &hvy_hdr, &hvy_buckets,
-                          &hvy_tasks, &hvy_partials, &treeS[0], &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum, &chunk_partials, &norm_in, &norm_out, &tile_sums, &size_hist, &endo})
+                          &hvy_tasks, &hvy_partials, &treeS[0], &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum, &chunk_partials, &norm_in, &norm_out, &tile_sums, &size_hist, &endo, &tbl_tmp})
             b->release();
     }
 };
@@ -202,7 +222,7 @@ DeviceCtx *ctx_for_current_device() {
 // `bases_ready` (optional): an event after which d_bases is valid — the scalar-side phases
 // (digits, sort, bucket offsets) do not read the bases, so they overlap the bases' H2D copy.
 int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scalars_v, size_t n, int mont, void *d_out_v,
-              cudaStream_t st, cudaEvent_t bases_ready = nullptr) {
+              cudaStream_t st, cudaEvent_t bases_ready = nullptr, const TableRef *tbl = nullptr) {
     if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "group must be B200MSM_G1 or B200MSM_G2");
     const bool g2 = group == B200MSM_G2;
     const uint32_t *d_bases = (const uint32_t *)d_bases_v, *d_scalars = (const uint32_t *)d_scalars_v;
@@ -214,7 +234,15 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
         return 0;
     }
     Plan pl;
-    auto_plan(n, g2, g_eng.glv_mode, std::min(g_eng.window_override, 22), pl);
+    if (tbl) {  // the table fixes the width
+        pl.c = tbl->c;
+        pl.nwin = tbl->nwin;
+        pl.glv = false;
+        pl.nbw = 1u << (pl.c - 1);
+        pl.nb = pl.nbw * (uint32_t)pl.nwin;   // (window, bucket) segments of the grouping; buckets: nbw
+        d_bases = (const uint32_t *)tbl->p;
+    } else auto_plan(n, g2, g_eng.glv_mode, std::min(g_eng.window_override, 22), pl);
+    const int rwin = tbl ? 1 : pl.nwin;       // windows the reduction sees
     const size_t entries = pl.glv ? 2 * n : n;  // per window
     const size_t m = entries * (size_t)pl.nwin;
     const bool prof = g_eng.profiling;
@@ -226,12 +254,12 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     if (int rc = cx.cnt.reserve((size_t)pl.nb * 4)) return rc;
     if (int rc = cx.ord.reserve((size_t)pl.nb * 4)) return rc;
     for (int i = 0; i < 2; i++) {
-        size_t lvl = (size_t)pl.nwin * std::max<size_t>(1, pl.nbw / 32) * PB;
+        size_t lvl = (size_t)rwin * std::max<size_t>(1, pl.nbw / 32) * PB;
         if (int rc = cx.lvlR[i].reserve(lvl)) return rc;
         if (int rc = cx.lvlC[i].reserve(lvl)) return rc;
     }
     if (int rc = cx.start.reserve(((size_t)pl.nb + 2) * 4)) return rc;
-    if (int rc = cx.buckets.reserve((size_t)pl.nb * PB)) return rc;
+    if (int rc = cx.buckets.reserve((size_t)pl.nbw * rwin * PB)) return rc;
     // heavy buckets: one thread per bucket is the efficient shape (≈0.31 product-times per entry
     // per warp vs ≈1 for the block-cooperative path), so a bucket only counts as heavy when its
     // serial chain would be a visible fraction (≈8 %) of the whole accumulation — the kernel lasts
@@ -244,7 +272,8 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     if (int rc = cx.hvy_hdr.reserve(16)) return rc;
     if (int rc = cx.hvy_buckets.reserve(max_heavy * 12)) return rc;
     if (int rc = cx.hvy_tasks.reserve(max_tasks * 8)) return rc;
-    if (int rc = cx.hvy_partials.reserve(max_tasks * PB)) return rc;
+    if (int rc = cx.hvy_partials.reserve((max_tasks + (tbl ? max_heavy : 0)) * PB)) return rc;
+    uint32_t *hvy_sums = cx.hvy_partials.as<uint32_t>() + max_tasks * (PB / 4);  // table mode: one sum per heavy segment
     uint32_t *vals = cx.vals.as<uint32_t>(), *ord = cx.ord.as<uint32_t>();
     uint32_t *start = cx.start.as<uint32_t>();
     if (int rc = cx.tile_sums.reserve(((size_t)pl.nb / 2048 + 4) * 4)) return rc;
@@ -258,7 +287,8 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     mark();
     mark();
     // 3. buckets in decreasing-size order (sizes above 4095 all sort first)
-    launch_order_by_size(start, pl.nb, cx.size_hist.as<uint32_t>(), ord, st);
+    if (tbl) launch_order_by_size(start, pl.nbw, cx.size_hist.as<uint32_t>(), ord, st, pl.nbw, pl.nwin);
+    else launch_order_by_size(start, pl.nb, cx.size_hist.as<uint32_t>(), ord, st);
     mark();
     // 4. bucket accumulation
     CUDA_TRY(cudaMemsetAsync(cx.hvy_hdr.p, 0, 16, st));
@@ -275,13 +305,24 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     // the SMs the other leaves idle at its tail
     CUDA_TRY(cudaEventRecord(cx.ev_fork, st));
     CUDA_TRY(cudaStreamWaitEvent(cx.aux_stream, cx.ev_fork, 0));
-    (g2 ? launch_heavy_g2 : launch_heavy_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, endo_x, n_pts, cx.hvy_hdr.p,
-                                             cx.hvy_buckets.p, cx.hvy_tasks.p, cx.hvy_partials.as<uint32_t>(),
-                                             cx.buckets.as<uint32_t>(), cx.sm_count * 4, cx.aux_stream);
-    CUDA_TRY(cudaEventRecord(cx.ev_join, cx.aux_stream));
-    (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, endo_x, n_pts,
-                                                       cx.buckets.as<uint32_t>(), st);
-    CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_join, 0));
+    if (tbl) {
+        (g2 ? launch_heavy_g2 : launch_heavy_g1)(d_bases, vals, start, nullptr, pl.nb, heavy_thr, nullptr, 0xffffffffu, cx.hvy_hdr.p,
+                                                 cx.hvy_buckets.p, cx.hvy_tasks.p, cx.hvy_partials.as<uint32_t>(), hvy_sums,
+                                                 cx.sm_count * 4, cx.aux_stream, pl.nbw, tbl->stride);
+        CUDA_TRY(cudaEventRecord(cx.ev_join, cx.aux_stream));
+        (g2 ? launch_accumulate_tbl_g2 : launch_accumulate_tbl_g1)(d_bases, tbl->stride, vals, start, ord, pl.nbw, pl.nwin, heavy_thr,
+                                                                   cx.buckets.as<uint32_t>(), st);
+        CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_join, 0));
+        (g2 ? launch_heavy_fold_g2 : launch_heavy_fold_g1)(cx.hvy_hdr.p, cx.hvy_buckets.p, hvy_sums, pl.nbw, cx.buckets.as<uint32_t>(), st);
+    } else {
+        (g2 ? launch_heavy_g2 : launch_heavy_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, endo_x, n_pts, cx.hvy_hdr.p,
+                                                 cx.hvy_buckets.p, cx.hvy_tasks.p, cx.hvy_partials.as<uint32_t>(),
+                                                 cx.buckets.as<uint32_t>(), cx.sm_count * 4, cx.aux_stream, 0, 0);
+        CUDA_TRY(cudaEventRecord(cx.ev_join, cx.aux_stream));
+        (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, endo_x, n_pts,
+                                                           cx.buckets.as<uint32_t>(), st);
+        CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_join, 0));
+    }
     mark();
     // 5. per-window weighted bucket sums: running-sum levels of fan-in 32 while the arrays are long
     //    (throughput-bound), then a log-depth tree (latency-bound part)
@@ -289,8 +330,9 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     const uint32_t *Cin = nullptr;
     uint32_t len = pl.nbw;
     int log2M = 0, pp = 0;
-    while (len > 2048) {
-        (g2 ? launch_wsum_level_g2 : launch_wsum_level_g1)(X, Cin, len, 32, log2M, (uint32_t)pl.nwin,
+    // (a single window — table mode — goes to the tree as soon as a level would leave fewer than 4096 chains)
+    while (len > 2048 && (!tbl || len / 32 >= 4096)) {
+        (g2 ? launch_wsum_level_g2 : launch_wsum_level_g1)(X, Cin, len, 32, log2M, (uint32_t)rwin,
                                                            cx.lvlR[pp].as<uint32_t>(), cx.lvlC[pp].as<uint32_t>(), st);
         X = cx.lvlR[pp].as<uint32_t>();
         Cin = cx.lvlC[pp].as<uint32_t>();
@@ -303,18 +345,18 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     while ((1u << logS) < S) logS++;
     const size_t tstride = std::max<uint32_t>(1, S / 2);  // points per window in every tree array
     for (int i = 0; i < 2; i++) {
-        if (int rc = cx.treeS[i].reserve((size_t)pl.nwin * tstride * PB)) return rc;
-        if (int rc = cx.treeV[i].reserve((size_t)pl.nwin * tstride * PB)) return rc;
-        if (int rc = cx.treeC[i].reserve((size_t)pl.nwin * tstride * PB)) return rc;
+        if (int rc = cx.treeS[i].reserve((size_t)rwin * tstride * PB)) return rc;
+        if (int rc = cx.treeV[i].reserve((size_t)rwin * tstride * PB)) return rc;
+        if (int rc = cx.treeC[i].reserve((size_t)rwin * tstride * PB)) return rc;
     }
-    if (int rc = cx.wsum.reserve((size_t)pl.nwin * PB)) return rc;
+    if (int rc = cx.wsum.reserve((size_t)rwin * PB)) return rc;
     const uint32_t *Sin = X, *Ccur = Cin;
     size_t sin_stride = S, cin_stride = S;
     int cur = 0;
     for (int j = 0; j < logS; j++) {
         (g2 ? launch_tree_level_g2 : launch_tree_level_g1)(Sin, sin_stride, cx.treeV[cur].as<uint32_t>(), Ccur, cin_stride,
                                                            cx.treeS[cur ^ 1].as<uint32_t>(), cx.treeV[cur ^ 1].as<uint32_t>(),
-                                                           cx.treeC[cur ^ 1].as<uint32_t>(), tstride, S, j, (uint32_t)pl.nwin, st);
+                                                           cx.treeC[cur ^ 1].as<uint32_t>(), tstride, S, j, (uint32_t)rwin, st);
         cur ^= 1;
         Sin = cx.treeS[cur].as<uint32_t>();
         sin_stride = tstride;
@@ -323,7 +365,7 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     mark();
     // 6. window values and Horner over the windows → one Jacobian point
     (g2 ? launch_combine_g2 : launch_combine_g1)(Sin, cx.treeV[cur].as<uint32_t>(), Cin ? Ccur : nullptr, tstride, logS, log2M,
-                                                 pl.nwin, pl.c, cx.wsum.as<uint32_t>(), d_out, st);
+                                                 rwin, pl.c, cx.wsum.as<uint32_t>(), d_out, st);
     mark();
     CUDA_TRY(cudaGetLastError());
     cx.phase_pending = prof;  // elapsed times are read lazily by b200msm_last_phase_ms (no sync here)
@@ -331,11 +373,12 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
 }
 
 // Scratch bytes one pass over n points needs (sort double buffers dominate).
-size_t pass_scratch_bytes(size_t n, bool g2, int c_override) {
+size_t pass_scratch_bytes(size_t n, bool g2, int c_override, bool table = false) {
     int c = c_override > 0 ? c_override : auto_window(n, g2);
     c = std::max(2, std::min(c, 24));
     size_t nwin = (256 + c - 1) / c, nb = nwin << (c - 1), m = n * nwin;  // the GLV plan needs about the same
     size_t PB = g2 ? 384 : 192;
+    if (table) return m * 8 + nb * 20 + (nb / nwin) * (PB + PB / 8) + m / 96 * (PB + 20) + (64u << 20);
     return m * 8 + nb * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + n * 48 + (64u << 20);
 }
 
@@ -344,7 +387,7 @@ size_t pass_scratch_bytes(size_t n, bool g2, int c_override) {
 // are cut into equal chunks whose sort arrays stay below 2^32 entries and within the free HBM,
 // each chunk yields a Jacobian partial, and the partials are added on the device.
 int run_group(int group, DeviceCtx &cx, const void *d_bases, const void *d_scalars, size_t n, int mont, void *d_out,
-              cudaStream_t st, cudaEvent_t bases_ready = nullptr) {
+              cudaStream_t st, cudaEvent_t bases_ready = nullptr, const TableRef *tbl = nullptr) {
     if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "group must be B200MSM_G1 or B200MSM_G2");
     const bool g2 = group == B200MSM_G2;
     // GPU-side serialisation of the context's scratch arena across streams
@@ -352,7 +395,7 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases, const void *d_scala
     // cudaMemGetInfo is a slow synchronous driver call (≈0.3–1 ms): only ask for sizes that have
     // not already run as a single pass on this context (the grow-only arena then fits)
     size_t budget = ~(size_t)0;
-    if (!g_eng.max_chunk_override && n > cx.fits_n[g2 ? 1 : 0]) {
+    if (!g_eng.max_chunk_override && (tbl || n > cx.fits_n[g2 ? 1 : 0])) {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         budget = (size_t)((double)(free_b + cx.scratch_bytes()) * 0.85);
@@ -360,6 +403,7 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases, const void *d_scala
     size_t chunks = 1;
     auto too_big = [&](size_t cn) {
         if (g_eng.max_chunk_override) return cn > g_eng.max_chunk_override;
+        if (tbl) return cn * tbl->nwin >= 0xfff00000ull || pass_scratch_bytes(cn, g2, tbl->c, true) > budget;
         Plan p;
         auto_plan(cn, g2, g_eng.glv_mode, std::min(g_eng.window_override, 22), p);
         size_t ent = (p.glv ? 2 : 1) * cn;
@@ -371,15 +415,17 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases, const void *d_scala
     }
     int rc = 0;
     if (chunks == 1) {
-        rc = run_pass(group, cx, d_bases, d_scalars, n, mont, d_out, st, bases_ready);
-        if (!rc && !g_eng.max_chunk_override && g_eng.window_override == 0) cx.fits_n[g2 ? 1 : 0] = std::max(cx.fits_n[g2 ? 1 : 0], n);
+        rc = run_pass(group, cx, d_bases, d_scalars, n, mont, d_out, st, bases_ready, tbl);
+        if (!rc && !tbl && !g_eng.max_chunk_override && g_eng.window_override == 0) cx.fits_n[g2 ? 1 : 0] = std::max(cx.fits_n[g2 ? 1 : 0], n);
     } else {
         const size_t AB = g2 ? 192 : 96, JB = g2 ? 288 : 144;
         if ((rc = cx.chunk_partials.reserve(chunks * JB))) return rc;
         for (size_t k = 0; k < chunks && !rc; k++) {
             size_t lo = n * k / chunks, hi = n * (k + 1) / chunks;
+            TableRef sub;
+            if (tbl) { sub = *tbl; sub.p = (const char *)tbl->p + lo * AB; }  // same stride, shifted origin
             rc = run_pass(group, cx, (const char *)d_bases + lo * AB, (const char *)d_scalars + lo * 32, hi - lo, mont,
-                          (char *)cx.chunk_partials.p + k * JB, st, k == 0 ? bases_ready : nullptr);
+                          (char *)cx.chunk_partials.p + k * JB, st, k == 0 ? bases_ready : nullptr, tbl ? &sub : nullptr);
         }
         if (!rc) (g2 ? launch_sum_partials_g2 : launch_sum_partials_g1)((const uint32_t *)cx.chunk_partials.p, (int)chunks, (uint32_t *)d_out, st);
     }
@@ -393,6 +439,29 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases, const void *d_scala
 size_t aff_bytes(int group) { return group == B200MSM_G2 ? 192 : 96; }
 size_t jac_bytes(int group) { return group == B200MSM_G2 ? 288 : 144; }
 
+// Windows 1..nwin−1 of a fixed-base table whose window 0 (the bases themselves) is already in
+// place: table[w] = 2^c·table[w−1], c doublings per point then a batch normalisation back to
+// affine, in slices that bound the Jacobian scratch.  ctx.mu held, ctx.dev current, async on st.
+int build_table(int group, DeviceCtx &cx, void *d_table, size_t n, size_t stride, int c, int nwin, cudaStream_t st) {
+    const bool g2 = group == B200MSM_G2;
+    const size_t AB = aff_bytes(group), JB = jac_bytes(group);
+    const size_t slice = std::min<size_t>(n, (size_t)1 << 22);
+    if (cx.busy_valid) CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_busy, 0));
+    if (int rc = cx.tbl_tmp.reserve(slice * JB)) return rc;
+    for (int w = 1; w < nwin; w++)
+        for (size_t lo = 0; lo < n; lo += slice) {
+            const size_t cn = std::min(slice, n - lo);
+            const uint32_t *prev = (const uint32_t *)((const char *)d_table + ((size_t)(w - 1) * stride + lo) * AB);
+            uint32_t *next = (uint32_t *)((char *)d_table + ((size_t)w * stride + lo) * AB);
+            (g2 ? launch_table_shift_g2 : launch_table_shift_g1)(prev, cn, c, cx.tbl_tmp.as<uint32_t>(), st);
+            launch_normalize_batch(g2, cx.tbl_tmp.as<uint32_t>(), cn, next, cx.sm_count, st);
+        }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(cx.ev_busy, st));
+    cx.busy_valid = true;
+    return 0;
+}
+
 // host-buffer MSM over the bound devices: shard by index range, one partial per device, final
 // addition on the first device.
 int msm_host(int group, const uint64_t *bases, const uint64_t *scalars, size_t n, int mont, uint64_t *out,
@@ -405,6 +474,9 @@ struct b200msm_bases {
     size_t n;
     std::vector<DevBuf> shard;      // one per bound device
     std::vector<size_t> lo, cnt;    // index range per device
+    // after b200msm_bases_precompute: window-major table per device (window 0 = the shard, which is then released)
+    std::vector<DevBuf> table;
+    int tbl_c = 0, tbl_nwin = 0;
 };
 
 namespace {
@@ -453,7 +525,11 @@ int msm_host(int group, const uint64_t *bases, const uint64_t *scalars, size_t n
         cudaStreamWaitEvent(cx.stream, cx.ev_scalars, 0);
         const void *db;
         cudaEvent_t ready = nullptr;
-        if (resident) db = resident->shard[d].p;
+        TableRef tr{nullptr, 0, 0, 0};
+        if (resident && resident->tbl_c) {
+            tr = TableRef{resident->table[d].p, resident->cnt[d], resident->tbl_c, resident->tbl_nwin};
+            db = tr.p;
+        } else if (resident) db = resident->shard[d].p;
         else {
             if ((rc = cx.bases.reserve(cnt[d] * AB))) break;
             cudaMemcpyAsync(cx.bases.p, (const char *)bases + lo[d] * AB, cnt[d] * AB, cudaMemcpyHostToDevice, cx.copy_stream);
@@ -461,7 +537,7 @@ int msm_host(int group, const uint64_t *bases, const uint64_t *scalars, size_t n
             db = cx.bases.p;
             ready = cx.ev_bases;
         }
-        rc = run_group(group, cx, db, cx.scalars.p, cnt[d], mont, cx.out.p, cx.stream, ready);
+        rc = run_group(group, cx, db, cx.scalars.p, cnt[d], mont, cx.out.p, cx.stream, ready, tr.c ? &tr : nullptr);
     }
     if (!rc) {
         DeviceCtx &c0 = *g_eng.ctx[0];
@@ -573,6 +649,7 @@ int b200msm_bases_free(b200msm_bases *h) {
     for (size_t d = 0; d < h->shard.size() && d < g_eng.ctx.size(); d++) {
         cudaSetDevice(g_eng.ctx[d]->dev);
         h->shard[d].release();
+        if (d < h->table.size()) h->table[d].release();
     }
     cudaSetDevice(prev);
     delete h;
@@ -582,6 +659,93 @@ int b200msm_run(const b200msm_bases *h, const uint64_t *scalars, size_t n, int m
     if (!h) return fail(B200MSM_EINVAL, "null handle");
     if (n > h->n) return fail(B200MSM_EINVAL, "n exceeds the uploaded base count");
     return msm_host(h->group, nullptr, scalars, n, mont, out, h);
+}
+
+int b200msm_table_plan(int group, size_t n, int *window_bits, int *windows) {
+    if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "bad group");
+    if (!window_bits || !windows) return fail(B200MSM_EINVAL, "null pointer");
+    int c = *window_bits;
+    if (c == 0) c = table_plan(std::max<size_t>(n, 1), group == B200MSM_G2);
+    if (c < 2 || c > 23) return fail(B200MSM_EINVAL, "table window bits must be 0 (auto) or 2..23");
+    *window_bits = c;
+    *windows = (256 + c - 1) / c;
+    return 0;
+}
+int b200msm_bases_precompute(b200msm_bases *h, int window_bits) {
+    if (!h) return fail(B200MSM_EINVAL, "null handle");
+    if (h->tbl_c) return 0;  // already a table
+    if (int rc = engine_init(-1, 1)) return rc;
+    const int ndev = (int)std::min(g_eng.ctx.size(), h->shard.size());
+    size_t maxcnt = 0;
+    for (int d = 0; d < ndev; d++) maxcnt = std::max(maxcnt, h->cnt[d]);
+    int c = window_bits, nwin = 0;
+    if (int rc = b200msm_table_plan(h->group, maxcnt, &c, &nwin)) return rc;
+    const size_t AB = aff_bytes(h->group);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    h->table.resize(h->shard.size());
+    int rc = 0;
+    for (int d = 0; d < ndev && !rc; d++) {
+        if (h->cnt[d] == 0) continue;
+        DeviceCtx &cx = *g_eng.ctx[d];
+        std::lock_guard<std::mutex> lk(cx.mu);
+        cudaSetDevice(cx.dev);
+        if ((rc = h->table[d].reserve((size_t)nwin * h->cnt[d] * AB))) break;
+        cudaMemcpyAsync(h->table[d].p, h->shard[d].p, h->cnt[d] * AB, cudaMemcpyDeviceToDevice, cx.stream);
+        rc = build_table(h->group, cx, h->table[d].p, h->cnt[d], h->cnt[d], c, nwin, cx.stream);
+    }
+    for (int d = 0; d < ndev; d++) {
+        if (h->cnt[d] == 0) continue;
+        DeviceCtx &cx = *g_eng.ctx[d];
+        cudaSetDevice(cx.dev);
+        cudaError_t e = cudaStreamSynchronize(cx.stream);
+        if (e != cudaSuccess && !rc) rc = fail(B200MSM_ECUDA, std::string("precompute: ") + cudaGetErrorString(e));
+    }
+    if (rc) {
+        for (int d = 0; d < ndev; d++) { cudaSetDevice(g_eng.ctx[d]->dev); h->table[d].release(); }
+    } else {
+        for (int d = 0; d < ndev; d++) { cudaSetDevice(g_eng.ctx[d]->dev); h->shard[d].release(); }
+        h->tbl_c = c;
+        h->tbl_nwin = nwin;
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+int b200msm_bases_table_info(const b200msm_bases *h, int *window_bits, int *windows, size_t *device_bytes) {
+    if (!h) return fail(B200MSM_EINVAL, "null handle");
+    if (window_bits) *window_bits = h->tbl_c;
+    if (windows) *windows = h->tbl_nwin;
+    if (device_bytes) {
+        size_t b = 0;
+        for (auto &t : h->table) b += t.cap;
+        for (auto &t : h->shard) b += t.cap;
+        *device_bytes = b;
+    }
+    return 0;
+}
+int b200msm_table_build_device(int group, const void *d_bases, size_t n, int window_bits, void *d_table, void *stream) {
+    if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "bad group");
+    if (n == 0) return 0;
+    if (!d_bases || !d_table) return fail(B200MSM_EINVAL, "null pointer");
+    if (window_bits < 2 || window_bits > 23) return fail(B200MSM_EINVAL, "table window bits must be 2..23 (see b200msm_table_plan)");
+    if (int rc = engine_init(-1, 1)) return rc;
+    DeviceCtx *cx = ctx_for_current_device();
+    if (!cx) return fail(B200MSM_EINVAL, "current device is not bound to the engine");
+    std::lock_guard<std::mutex> lk(cx->mu);
+    if (d_table != d_bases)
+        CUDA_TRY(cudaMemcpyAsync(d_table, d_bases, n * aff_bytes(group), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return build_table(group, *cx, d_table, n, n, window_bits, (256 + window_bits - 1) / window_bits, (cudaStream_t)stream);
+}
+int b200msm_run_table_device(int group, const void *d_table, size_t stride, int window_bits, const void *d_scalars, size_t n,
+                             int mont, void *d_out, void *stream) {
+    if (!d_out || (n && (!d_table || !d_scalars))) return fail(B200MSM_EINVAL, "null pointer");
+    if (window_bits < 2 || window_bits > 23 || n > stride) return fail(B200MSM_EINVAL, "bad table description");
+    if (int rc = engine_init(-1, 1)) return rc;
+    DeviceCtx *cx = ctx_for_current_device();
+    if (!cx) return fail(B200MSM_EINVAL, "current device is not bound to the engine");
+    std::lock_guard<std::mutex> lk(cx->mu);
+    TableRef tr{d_table, stride, window_bits, (256 + window_bits - 1) / window_bits};
+    return run_group(group, *cx, d_table, d_scalars, n, mont, d_out, (cudaStream_t)stream, nullptr, &tr);
 }
 
 int b200msm_run_device(int group, const void *d_bases, const void *d_scalars, size_t n, int mont, void *d_out,

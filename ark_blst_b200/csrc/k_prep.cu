@@ -135,8 +135,14 @@ k_scan_add(uint32_t *__restrict__ out, size_t n, const uint32_t *__restrict__ ti
 
 // ---- buckets ordered by decreasing size: one counting-sort pass on min(count, SIZE_BINS-1) ------
 constexpr int SIZE_BINS = 4096, SIZE_THREADS = 256, SIZE_ITEMS = 4;
+// entries of bucket b; table mode: summed over the fold_n windows' segments
+__device__ __forceinline__ uint32_t bucket_size(const uint32_t *__restrict__ start, uint32_t b, uint32_t fold_stride, int fold_n) {
+    uint32_t cn = 0;
+    for (int w = 0; w < fold_n; w++) cn += start[(size_t)w * fold_stride + b + 1] - start[(size_t)w * fold_stride + b];
+    return cn;
+}
 __global__ void __launch_bounds__(SIZE_THREADS)
-k_size_hist(const uint32_t *__restrict__ start, uint32_t nb, uint32_t *__restrict__ hist) {
+k_size_hist(const uint32_t *__restrict__ start, uint32_t nb, uint32_t fold_stride, int fold_n, uint32_t *__restrict__ hist) {
     __shared__ uint32_t lh[SIZE_BINS];
     for (int k = threadIdx.x; k < SIZE_BINS; k += SIZE_THREADS) lh[k] = 0;
     __syncthreads();
@@ -145,7 +151,7 @@ k_size_hist(const uint32_t *__restrict__ start, uint32_t nb, uint32_t *__restric
     for (int k = 0; k < SIZE_ITEMS; k++) {
         uint32_t b = b0 + k;
         if (b < nb) {
-            uint32_t cn = start[b + 1] - start[b];
+            uint32_t cn = bucket_size(start, b, fold_stride, fold_n);
             atomicAdd(&lh[cn < SIZE_BINS - 1 ? cn : SIZE_BINS - 1], 1u);
         }
     }
@@ -166,8 +172,8 @@ k_size_scan(const uint32_t *__restrict__ hist, uint32_t *__restrict__ binstart) 
     }
 }
 __global__ void __launch_bounds__(SIZE_THREADS)
-k_size_scatter(const uint32_t *__restrict__ start, uint32_t nb, uint32_t *__restrict__ bincursor,
-               uint32_t *__restrict__ order) {
+k_size_scatter(const uint32_t *__restrict__ start, uint32_t nb, uint32_t fold_stride, int fold_n,
+               uint32_t *__restrict__ bincursor, uint32_t *__restrict__ order) {
     __shared__ uint32_t lh[SIZE_BINS];   // local count, then global base of this block's run per bin
     for (int k = threadIdx.x; k < SIZE_BINS; k += SIZE_THREADS) lh[k] = 0;
     __syncthreads();
@@ -178,7 +184,7 @@ k_size_scatter(const uint32_t *__restrict__ start, uint32_t nb, uint32_t *__rest
         uint32_t b = b0 + k;
         bin[k] = 0xffffffffu;
         if (b < nb) {
-            uint32_t cn = start[b + 1] - start[b];
+            uint32_t cn = bucket_size(start, b, fold_stride, fold_n);
             bin[k] = cn < SIZE_BINS - 1 ? cn : SIZE_BINS - 1;
             rank[k] = atomicAdd(&lh[bin[k]], 1u);
         }
@@ -206,13 +212,14 @@ void launch_group_by_bucket(const uint32_t *scalars, size_t n, int mont, int glv
     k_scatter<<<dim3(blocks_for(entries, 256), (unsigned)nwin), 256, 0, st>>>(dig, entries, c, start, count, vals);
 }
 // hist: 2·SIZE_BINS u32 of scratch
-void launch_order_by_size(const uint32_t *start, uint32_t nb, uint32_t *hist, uint32_t *order, cudaStream_t st) {
+void launch_order_by_size(const uint32_t *start, uint32_t nb, uint32_t *hist, uint32_t *order, cudaStream_t st,
+                          uint32_t fold_stride, int fold_n) {
     for (int k = 0; k < 3; k++) count_launch();
     cudaMemsetAsync(hist, 0, SIZE_BINS * 4, st);
     unsigned blocks = blocks_for(nb, SIZE_THREADS * SIZE_ITEMS);
-    k_size_hist<<<blocks, SIZE_THREADS, 0, st>>>(start, nb, hist);
+    k_size_hist<<<blocks, SIZE_THREADS, 0, st>>>(start, nb, fold_stride, fold_n, hist);
     k_size_scan<<<1, SCAN_THREADS, 0, st>>>(hist, hist + SIZE_BINS);
-    k_size_scatter<<<blocks, SIZE_THREADS, 0, st>>>(start, nb, hist + SIZE_BINS, order);
+    k_size_scatter<<<blocks, SIZE_THREADS, 0, st>>>(start, nb, fold_stride, fold_n, hist + SIZE_BINS, order);
 }
 
 void launch_digits_dbg(const uint32_t *scalars, size_t n, int mont, int c, int nwin, int *out, cudaStream_t st) {

@@ -129,7 +129,8 @@ k_combine(const uint32_t *__restrict__ Sroot, const uint32_t *__restrict__ V, co
     if (threadIdx.x >= 32) return;                 // warp 0 finishes (its 8 quads in lock-step)
     q_set_inf(acc);
     for (int ww = nwin - 1; ww >= 0; ww--) {
-        for (int k = 0; k < c; k++) q_dbl(acc);
+        if (ww != nwin - 1)                        // nothing to double before the top window
+            for (int k = 0; k < c; k++) q_dbl(acc);
         q_load(a, wsum + (size_t)ww * PW);
         q_add(acc, a);
     }

@@ -131,6 +131,14 @@ class ResidentBases:
         self._h = ctypes.c_void_p()
         _lib.check(lib.b200msm_bases_upload(group_cls.GROUP, _ptr(bases), self.n, ctypes.byref(self._h)), "bases_upload")
 
+    def precompute(self, window_bits=0):
+        """Turn the resident bases into a fixed-base window table (table[w][i] = 2^(c·w)·P_i): later
+        msm() calls use one bucket set for all windows and no Horner chain. Returns (c, windows, bytes)."""
+        _lib.check(lib.b200msm_bases_precompute(self._h, int(window_bits)), "bases_precompute")
+        c, w, b = ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
+        _lib.check(lib.b200msm_bases_table_info(self._h, ctypes.byref(c), ctypes.byref(w), ctypes.byref(b)), "bases_table_info")
+        return c.value, w.value, b.value
+
     def msm(self, scalars, montgomery=True):
         scalars = _u64(scalars, 4)
         if scalars.shape[0] > self.n:
@@ -156,6 +164,22 @@ class ResidentBases:
 # ---- device-pointer helpers (torch tensors / raw pointers already in HBM) ----
 def run_device(group, d_bases, d_scalars, n, montgomery, d_out, stream=0):
     _lib.check(lib.b200msm_run_device(group, d_bases, d_scalars, n, int(montgomery), d_out, stream), "run_device")
+
+
+def table_plan(group, n, window_bits=0):
+    """(c, windows) of the fixed-base table for n points; the table holds windows × n affine points"""
+    c, w = ctypes.c_int(int(window_bits)), ctypes.c_int()
+    _lib.check(lib.b200msm_table_plan(group, n, ctypes.byref(c), ctypes.byref(w)), "table_plan")
+    return c.value, w.value
+
+
+def table_build_device(group, d_bases, n, window_bits, d_table, stream=0):
+    _lib.check(lib.b200msm_table_build_device(group, d_bases, n, int(window_bits), d_table, stream), "table_build_device")
+
+
+def run_table_device(group, d_table, stride, window_bits, d_scalars, n, montgomery, d_out, stream=0):
+    _lib.check(lib.b200msm_run_table_device(group, d_table, stride, int(window_bits), d_scalars, n, int(montgomery), d_out, stream),
+               "run_table_device")
 
 
 def sum_partials_device(group, d_partials, count, d_out, stream=0):

@@ -77,6 +77,28 @@ int b200msm_bases_free(b200msm_bases *handle);
 int b200msm_run(const b200msm_bases *handle, const uint64_t *scalars, size_t n,
                 int scalars_are_montgomery, uint64_t *out /*18 or 36 u64*/);
 
+/* Fixed-base window table for resident bases ("upload a proving key once, run many
+ * scalar vectors"): converts an uploaded handle in place into table[w][i] = 2^(c·w)·P_i (affine,
+ * W = ceil(256/c) windows, W× the memory of the bases).  Every later b200msm_run on the handle
+ * then accumulates all windows into ONE bucket set: the bucket reduction covers a single window
+ * and the on-device Horner chain (255 dependent doublings) disappears; results are the same group
+ * elements.  window_bits = 0 picks the width from the shard size.  One-time cost: ≈ 256 point
+ * doublings + one batch normalisation per base.  The reference has no counterpart (it rebuilds
+ * even its kernel per call, src/gpu.rs:233-237); provers that reuse a proving key are the use. */
+int b200msm_bases_precompute(b200msm_bases *handle, int window_bits);
+int b200msm_bases_table_info(const b200msm_bases *handle, int *window_bits, int *windows,
+                             size_t *device_bytes);
+/* Device-pointer forms of the same: *window_bits = 0 → automatic for n; returns the window count
+ * so the caller can allocate d_table = windows × n affine points.  d_bases may alias d_table's
+ * first window.  run_table: `stride` = points per window of the table (the n it was built for);
+ * n ≤ stride uses the prefix. */
+int b200msm_table_plan(int group, size_t n, int *window_bits, int *windows);
+int b200msm_table_build_device(int group, const void *d_bases, size_t n, int window_bits,
+                               void *d_table, void *stream);
+int b200msm_run_table_device(int group, const void *d_table, size_t stride, int window_bits,
+                             const void *d_scalars, size_t n, int scalars_are_montgomery,
+                             void *d_out, void *stream);
+
 /* Device-pointer form for callers that already hold the inputs in HBM on the CURRENT device
  * (bench.py's kernel-only figure; torch tensors via data_ptr()).  `d_out` is a device buffer of
  * 18/36 u64; the call is asynchronous on `stream` (a cudaStream_t, 0 = default). */
