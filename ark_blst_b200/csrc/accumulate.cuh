@@ -19,7 +19,7 @@ struct HeavyBucket {
     uint32_t bucket, task_base, n_tasks;
 };
 struct HeavyTask {
-    uint32_t offset, len_win;  // slice of the sorted value array: len (≤ HEAVY_CHUNK) | window ≪ 16 (table mode)
+    uint32_t offset, len;  // slice of the sorted value array
 };
 
 // ---- light buckets: the hot kernel -----------------------------------------------------------
@@ -70,55 +70,8 @@ k_accumulate(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ va
 // With table[w][i] = 2^(c·w)·P_i stored in affine form, Σ_w 2^(cw)·Σ_i d_{w,i}·P_i becomes
 // Σ_{w,i} d_{w,i}·table[w][i]: ONE bucket set shared by all windows, so the bucket reduction runs
 // over a single window and the 255 dependent doublings of the Horner chain disappear.  The
-// grouping is unchanged — entries stay grouped by (window, bucket) segment — and the thread that
-// owns bucket b walks its segment in every window, reading window w's slice of the table.
-// `order` ranks the nbw buckets by their size summed over the windows.  Segments above heavy_thr
-// are left to the block-cooperative path, whose sums k_heavy_fold adds afterwards.
-template <class F>
-__global__ void __launch_bounds__(128, (field_words<F>::value == 12 ? 3 : 2))  // G1: three blocks per SM need ≤ 168 registers
-k_accumulate_tbl(const uint32_t *__restrict__ table, size_t stride, const uint32_t *__restrict__ vals,
-                 const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, uint32_t nbw, int nwin,
-                 uint32_t heavy_thr, uint32_t *__restrict__ buckets) {
-    constexpr int W = field_words<F>::value;
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nbw) return;
-    const uint32_t b = order[t];
-    xyzz<F> acc;
-    xyzz_set_inf(acc);
-    // one flat loop over the entries of all windows' segments, so the madd body exists once
-    int w = 0;
-    uint32_t j = 0, e = 0;
-    const uint32_t *base = table;
-    for (;;) {
-        while (j >= e) {                       // next non-empty light segment
-            if (w >= nwin) goto done;
-            j = start[(size_t)w * nbw + b];
-            e = start[(size_t)w * nbw + b + 1];
-            if (e - j > heavy_thr) e = j;      // heavy segment: not ours
-            base = table + (size_t)w * stride * (2 * W);
-            w++;
-        }
-        {
-            const uint32_t v = vals[j];
-            const uint32_t *p = base + (size_t)(v & 0x7fffffffu) * (2 * W);
-            F x, y;
-            f_load(x, p);
-            f_load(y, p + W);
-            j++;
-            if (j < e) {                       // pull the next point towards L1 while this one is being added
-                const char *q = reinterpret_cast<const char *>(base + (size_t)(vals[j] & 0x7fffffffu) * (2 * W));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(q + 8 * W - 4));
-            }
-            if (f_is_zero(x) && f_is_zero(y)) continue;  // identity base
-            f_cneg(y, y, v >> 31);
-            xyzz_madd(acc, x, y);
-        }
-    }
-done:
-    xyzz_store(buckets + (size_t)b * (4 * W), acc);
-}
-
+// grouping kernels then group by the digit alone and emit the table index w·stride + i, and the
+// kernels above run unchanged with `bases` = the table (k_prep.cu: k_hist / k_scatter, tbl_stride).
 // table[w] from table[w−1]: c doublings of every point, written as Jacobian for the batch
 // normalisation that follows (one launch pair per window; runs once per uploaded key)
 template <class F>
@@ -159,12 +112,10 @@ k_endo_table(const uint32_t *__restrict__ bases, size_t n, uint32_t *__restrict_
 // one thread per bucket rank: heavy ones claim a slot and a run of tasks of ≤ chunk entries
 static __global__ void __launch_bounds__(256)
 k_plan_heavy(const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, uint32_t nb, uint32_t heavy_thr,
-             uint32_t chunk, uint32_t nbw_tbl, HeavyHeader *__restrict__ hdr, HeavyBucket *__restrict__ hb,
-             HeavyTask *__restrict__ tasks) {
+             uint32_t chunk, HeavyHeader *__restrict__ hdr, HeavyBucket *__restrict__ hb, HeavyTask *__restrict__ tasks) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nb) return;
-    uint32_t b = order ? order[t] : t;         // table mode: every (window, bucket) segment, no order array
-    const uint32_t win = nbw_tbl ? b / nbw_tbl : 0;
+    uint32_t b = order[t];
     uint32_t s = start[b], cnt = start[b + 1] - s;
     if (cnt <= heavy_thr) return;
     uint32_t nt = (cnt + chunk - 1) / chunk;
@@ -173,7 +124,7 @@ k_plan_heavy(const uint32_t *__restrict__ start, const uint32_t *__restrict__ or
     hb[slot] = HeavyBucket{b, base, nt};
     for (uint32_t k = 0; k < nt; k++) {
         uint32_t off = k * chunk;
-        tasks[base + k] = HeavyTask{s + off, (cnt - off < chunk ? cnt - off : chunk) | (win << 16)};
+        tasks[base + k] = HeavyTask{s + off, cnt - off < chunk ? cnt - off : chunk};
     }
 }
 
@@ -187,7 +138,7 @@ __device__ __forceinline__ void block_tree_sum(xyzz<F> &acc, uint32_t *smem) {
         if ((int)threadIdx.x < stride) {
             xyzz<F> o;
             xyzz_load(o, smem + (size_t)threadIdx.x * PW);
-            xyzz_add_ni(acc, o);
+            xyzz_add(acc, o);                         // inlined: both operands stay in registers
         }
         __syncthreads();
     }
@@ -198,23 +149,21 @@ template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_heavy_tasks(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ vals,
               const HeavyHeader *__restrict__ hdr, const HeavyTask *__restrict__ tasks, const uint32_t *__restrict__ endo_x,
-              uint32_t n_pts, size_t tbl_stride, uint32_t *__restrict__ partials) {
+              uint32_t n_pts, uint32_t *__restrict__ partials) {
     constexpr int W = field_words<F>::value;
     constexpr int PW = 4 * W;
     __shared__ __align__(16) uint32_t smem[(THREADS / 2) * PW];
     const uint32_t nt = hdr->n_tasks;
     for (uint32_t t = blockIdx.x; t < nt; t += gridDim.x) {
         HeavyTask tk = tasks[t];
-        const uint32_t len = tk.len_win & 0xffffu;
-        const uint32_t *wbase = bases + (size_t)(tk.len_win >> 16) * tbl_stride * (2 * W);  // table mode: the window's slice
         xyzz<F> acc;
         xyzz_set_inf(acc);
-        for (uint32_t j = threadIdx.x; j < len; j += THREADS) {
+        for (uint32_t j = threadIdx.x; j < tk.len; j += THREADS) {
             uint32_t v = vals[tk.offset + j];
             uint32_t idx = v & 0x7fffffffu;
             const bool endo = idx >= n_pts;
             if (endo) idx -= n_pts;
-            const uint32_t *p = wbase + (size_t)idx * (2 * W);
+            const uint32_t *p = bases + (size_t)idx * (2 * W);
             F x, y;
             f_load(x, endo ? endo_x + (size_t)idx * W : p);
             f_load(y, p + W);
@@ -231,7 +180,7 @@ k_heavy_tasks(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ v
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_heavy_final(const HeavyHeader *__restrict__ hdr, const HeavyBucket *__restrict__ hb,
-              const uint32_t *__restrict__ partials, uint32_t *__restrict__ buckets, int by_slot) {
+              const uint32_t *__restrict__ partials, uint32_t *__restrict__ buckets) {
     constexpr int PW = 4 * field_words<F>::value;
     __shared__ __align__(16) uint32_t smem[(THREADS / 2) * PW];
     const uint32_t nh = hdr->n_heavy;
@@ -244,32 +193,7 @@ k_heavy_final(const HeavyHeader *__restrict__ hdr, const HeavyBucket *__restrict
             xyzz_add_ni(acc, o);
         }
         if (B.n_tasks > 1) block_tree_sum<F, THREADS>(acc, smem);  // block-uniform condition
-        // table mode: several heavy segments can share a bucket, so sums go to their slot first
-        if (threadIdx.x == 0) xyzz_store(buckets + (size_t)(by_slot ? h : B.bucket) * PW, acc);
-    }
-}
-
-// table mode: add the heavy segments' sums into their shared buckets, after the light kernel.
-// One thread per heavy slot; the first slot naming a bucket folds every slot that names it.
-template <class F>
-__global__ void __launch_bounds__(128)
-k_heavy_fold(const HeavyHeader *__restrict__ hdr, const HeavyBucket *__restrict__ hb, const uint32_t *__restrict__ sums,
-             uint32_t nbw, uint32_t *__restrict__ buckets) {
-    constexpr int PW = 4 * field_words<F>::value;
-    const uint32_t nh = hdr->n_heavy;
-    for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += gridDim.x * blockDim.x) {
-        const uint32_t b = hb[h].bucket % nbw;
-        bool first = true;
-        for (uint32_t k = 0; k < h && first; k++) first = hb[k].bucket % nbw != b;
-        if (!first) continue;
-        xyzz<F> acc, o;
-        xyzz_load(acc, buckets + (size_t)b * PW);
-        for (uint32_t k = h; k < nh; k++) {
-            if (hb[k].bucket % nbw != b) continue;
-            xyzz_load(o, sums + (size_t)k * PW);
-            xyzz_add_ni(acc, o);
-        }
-        xyzz_store(buckets + (size_t)b * PW, acc);
+        if (threadIdx.x == 0) xyzz_store(buckets + (size_t)B.bucket * PW, acc);
     }
 }
 

@@ -118,6 +118,11 @@ int table_plan(size_t n, bool g2) {
         const double W = std::ceil(256.0 / c);
         double t = (double)n * W * madd * 588 / (pipe * (g2 ? 0.76 : 0.88)) + std::pow(2.0, c - 1) * 2 * add * 588 / (pipe * 0.55) +
                    (double)n * W * 2.3e-5 + c * (g2 ? 40.0 : 16.0);
+        // the top window only holds 255 − (W−1)·c bits: when that is few, its n entries pile into a
+        // handful of buckets and go down the block-cooperative path (≈3.5× the cost per entry)
+        const int topbits = std::max(0, 255 - ((int)W - 1) * c);
+        const double m = (double)n * W, thr = std::max(std::max(32.0, 4 * m / std::pow(2.0, c - 1)), m / 175000);
+        if (topbits < c - 1 && (double)n / std::pow(2.0, topbits) > thr) t += (double)n * madd * 588 / pipe * 3.5;
         if (t < best) { best = t; bc = c; }
     }
     return bc;
@@ -135,6 +140,8 @@ struct DeviceCtx {
     cudaEvent_t ev_scalars = nullptr, ev_bases = nullptr, ev_busy = nullptr, ev_fork = nullptr, ev_join = nullptr;
     bool busy_valid = false;
     size_t fits_n[2] = {0, 0};  // largest n per group that already ran as a single pass (arena is big enough)
+    size_t fits_tbl_n[2] = {0, 0};  // same for the table path, valid for window width fits_tbl_c
+    int fits_tbl_c[2] = {0, 0};
     DevBuf bases, scalars, digits, vals, start, cnt, ord, buckets, lvlR[2], lvlC[2], out;
     DevBuf hvy_hdr, hvy_buckets, hvy_tasks, hvy_partials, treeS[2], treeV[2], treeC[2], wsum, chunk_partials, norm_in, norm_out, tile_sums, size_hist, endo, tbl_tmp;
     cudaEvent_t ev[8] = {};
@@ -166,6 +173,7 @@ struct Engine {
     size_t max_chunk_override = 0;
     int glv_mode = 0;   // -1 automatic (time model), 0 never (default: measured slower, see profiles/r01_experiments.md), 1 always (G1 only)
     bool profiling = false;
+    int heavy_factor = 0;  // a bucket is heavy above heavy_factor × the mean occupancy (see run_pass); 0 = automatic
 };
 Engine g_eng;
 
@@ -239,7 +247,7 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
         pl.nwin = tbl->nwin;
         pl.glv = false;
         pl.nbw = 1u << (pl.c - 1);
-        pl.nb = pl.nbw * (uint32_t)pl.nwin;   // (window, bucket) segments of the grouping; buckets: nbw
+        pl.nb = pl.nbw;                       // one bucket set shared by all windows
         d_bases = (const uint32_t *)tbl->p;
     } else auto_plan(n, g2, g_eng.glv_mode, std::min(g_eng.window_override, 22), pl);
     const int rwin = tbl ? 1 : pl.nwin;       // windows the reduction sees
@@ -259,21 +267,22 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
         if (int rc = cx.lvlC[i].reserve(lvl)) return rc;
     }
     if (int rc = cx.start.reserve(((size_t)pl.nb + 2) * 4)) return rc;
-    if (int rc = cx.buckets.reserve((size_t)pl.nbw * rwin * PB)) return rc;
+    if (int rc = cx.buckets.reserve((size_t)pl.nb * PB)) return rc;
     // heavy buckets: one thread per bucket is the efficient shape (≈0.31 product-times per entry
     // per warp vs ≈1 for the block-cooperative path), so a bucket only counts as heavy when its
     // serial chain would be a visible fraction (≈8 %) of the whole accumulation — the kernel lasts
     // ≈ m/175k bucket-entry times — or when it exceeds 3× the mean occupancy, whichever is larger.
     // Buckets are taken in decreasing-size order, so the long chains start first.
     // Worst-case list sizes follow from Σ counts = m.
-    const uint32_t avg = (uint32_t)((entries + pl.nbw - 1) / pl.nbw);
-    const uint32_t heavy_thr = std::max<uint32_t>(std::max<uint32_t>(32, 3 * avg), (uint32_t)(m / 175000));
+    // (table mode: the buckets the top window also feeds hold up to ≈2.3× the mean, so the factor is 4 there)
+    const uint32_t avg = (uint32_t)(((tbl ? m : entries) + pl.nbw - 1) / pl.nbw);
+    const int hfac = g_eng.heavy_factor ? g_eng.heavy_factor : (tbl ? 4 : 3);
+    const uint32_t heavy_thr = std::max<uint32_t>(std::max<uint32_t>(32, (uint32_t)hfac * avg), (uint32_t)(m / 175000));
     const size_t max_heavy = m / (heavy_thr + 1) + 1, max_tasks = m / HEAVY_CHUNK + max_heavy + 1;
     if (int rc = cx.hvy_hdr.reserve(16)) return rc;
     if (int rc = cx.hvy_buckets.reserve(max_heavy * 12)) return rc;
     if (int rc = cx.hvy_tasks.reserve(max_tasks * 8)) return rc;
-    if (int rc = cx.hvy_partials.reserve((max_tasks + (tbl ? max_heavy : 0)) * PB)) return rc;
-    uint32_t *hvy_sums = cx.hvy_partials.as<uint32_t>() + max_tasks * (PB / 4);  // table mode: one sum per heavy segment
+    if (int rc = cx.hvy_partials.reserve(max_tasks * PB)) return rc;
     uint32_t *vals = cx.vals.as<uint32_t>(), *ord = cx.ord.as<uint32_t>();
     uint32_t *start = cx.start.as<uint32_t>();
     if (int rc = cx.tile_sums.reserve(((size_t)pl.nb / 2048 + 4) * 4)) return rc;
@@ -283,12 +292,11 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     // 1+2. canonical scalars → window digits, per-bucket histogram, scan → bucket offsets, scatter
     //      of the point indices (a counting sort on the bucket id; zero digits are dropped)
     launch_group_by_bucket(d_scalars, n, mont, pl.glv ? 1 : 0, pl.c, pl.nwin, pl.nb, cx.digits.as<uint32_t>(), cx.cnt.as<uint32_t>(), start,
-                           cx.tile_sums.as<uint32_t>(), vals, st);
+                           cx.tile_sums.as<uint32_t>(), vals, st, tbl ? tbl->stride : 0);
     mark();
     mark();
     // 3. buckets in decreasing-size order (sizes above 4095 all sort first)
-    if (tbl) launch_order_by_size(start, pl.nbw, cx.size_hist.as<uint32_t>(), ord, st, pl.nbw, pl.nwin);
-    else launch_order_by_size(start, pl.nb, cx.size_hist.as<uint32_t>(), ord, st);
+    launch_order_by_size(start, pl.nb, cx.size_hist.as<uint32_t>(), ord, st);
     mark();
     // 4. bucket accumulation
     CUDA_TRY(cudaMemsetAsync(cx.hvy_hdr.p, 0, 16, st));
@@ -305,24 +313,13 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     // the SMs the other leaves idle at its tail
     CUDA_TRY(cudaEventRecord(cx.ev_fork, st));
     CUDA_TRY(cudaStreamWaitEvent(cx.aux_stream, cx.ev_fork, 0));
-    if (tbl) {
-        (g2 ? launch_heavy_g2 : launch_heavy_g1)(d_bases, vals, start, nullptr, pl.nb, heavy_thr, nullptr, 0xffffffffu, cx.hvy_hdr.p,
-                                                 cx.hvy_buckets.p, cx.hvy_tasks.p, cx.hvy_partials.as<uint32_t>(), hvy_sums,
-                                                 cx.sm_count * 4, cx.aux_stream, pl.nbw, tbl->stride);
-        CUDA_TRY(cudaEventRecord(cx.ev_join, cx.aux_stream));
-        (g2 ? launch_accumulate_tbl_g2 : launch_accumulate_tbl_g1)(d_bases, tbl->stride, vals, start, ord, pl.nbw, pl.nwin, heavy_thr,
-                                                                   cx.buckets.as<uint32_t>(), st);
-        CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_join, 0));
-        (g2 ? launch_heavy_fold_g2 : launch_heavy_fold_g1)(cx.hvy_hdr.p, cx.hvy_buckets.p, hvy_sums, pl.nbw, cx.buckets.as<uint32_t>(), st);
-    } else {
-        (g2 ? launch_heavy_g2 : launch_heavy_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, endo_x, n_pts, cx.hvy_hdr.p,
-                                                 cx.hvy_buckets.p, cx.hvy_tasks.p, cx.hvy_partials.as<uint32_t>(),
-                                                 cx.buckets.as<uint32_t>(), cx.sm_count * 4, cx.aux_stream, 0, 0);
-        CUDA_TRY(cudaEventRecord(cx.ev_join, cx.aux_stream));
-        (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, endo_x, n_pts,
-                                                           cx.buckets.as<uint32_t>(), st);
-        CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_join, 0));
-    }
+    (g2 ? launch_heavy_g2 : launch_heavy_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, endo_x, n_pts, cx.hvy_hdr.p,
+                                             cx.hvy_buckets.p, cx.hvy_tasks.p, cx.hvy_partials.as<uint32_t>(),
+                                             cx.buckets.as<uint32_t>(), cx.sm_count * 4, cx.aux_stream);
+    CUDA_TRY(cudaEventRecord(cx.ev_join, cx.aux_stream));
+    (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, endo_x, n_pts,
+                                                       cx.buckets.as<uint32_t>(), st);
+    CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_join, 0));
     mark();
     // 5. per-window weighted bucket sums: running-sum levels of fan-in 32 while the arrays are long
     //    (throughput-bound), then a log-depth tree (latency-bound part)
@@ -378,7 +375,7 @@ size_t pass_scratch_bytes(size_t n, bool g2, int c_override, bool table = false)
     c = std::max(2, std::min(c, 24));
     size_t nwin = (256 + c - 1) / c, nb = nwin << (c - 1), m = n * nwin;  // the GLV plan needs about the same
     size_t PB = g2 ? 384 : 192;
-    if (table) return m * 8 + nb * 20 + (nb / nwin) * (PB + PB / 8) + m / 96 * (PB + 20) + (64u << 20);
+    if (table) return m * 8 + (nb / nwin) * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + (64u << 20);
     return m * 8 + nb * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + n * 48 + (64u << 20);
 }
 
@@ -395,7 +392,9 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases, const void *d_scala
     // cudaMemGetInfo is a slow synchronous driver call (≈0.3–1 ms): only ask for sizes that have
     // not already run as a single pass on this context (the grow-only arena then fits)
     size_t budget = ~(size_t)0;
-    if (!g_eng.max_chunk_override && (tbl || n > cx.fits_n[g2 ? 1 : 0])) {
+    const int gi = g2 ? 1 : 0;
+    const bool known_fit = tbl ? (tbl->c == cx.fits_tbl_c[gi] && n <= cx.fits_tbl_n[gi]) : n <= cx.fits_n[gi];
+    if (!g_eng.max_chunk_override && !known_fit) {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         budget = (size_t)((double)(free_b + cx.scratch_bytes()) * 0.85);
@@ -416,7 +415,12 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases, const void *d_scala
     int rc = 0;
     if (chunks == 1) {
         rc = run_pass(group, cx, d_bases, d_scalars, n, mont, d_out, st, bases_ready, tbl);
-        if (!rc && !tbl && !g_eng.max_chunk_override && g_eng.window_override == 0) cx.fits_n[g2 ? 1 : 0] = std::max(cx.fits_n[g2 ? 1 : 0], n);
+        if (!rc && !g_eng.max_chunk_override) {
+            if (tbl) {
+                if (tbl->c != cx.fits_tbl_c[gi]) { cx.fits_tbl_c[gi] = tbl->c; cx.fits_tbl_n[gi] = 0; }
+                cx.fits_tbl_n[gi] = std::max(cx.fits_tbl_n[gi], n);
+            } else if (g_eng.window_override == 0) cx.fits_n[gi] = std::max(cx.fits_n[gi], n);
+        }
     } else {
         const size_t AB = g2 ? 192 : 96, JB = g2 ? 288 : 144;
         if ((rc = cx.chunk_partials.reserve(chunks * JB))) return rc;
@@ -667,6 +671,8 @@ int b200msm_table_plan(int group, size_t n, int *window_bits, int *windows) {
     int c = *window_bits;
     if (c == 0) c = table_plan(std::max<size_t>(n, 1), group == B200MSM_G2);
     if (c < 2 || c > 23) return fail(B200MSM_EINVAL, "table window bits must be 0 (auto) or 2..23");
+    if ((uint64_t)n * (uint64_t)((256 + c - 1) / c) >= (1ull << 31))
+        return fail(B200MSM_EINVAL, "table too large: windows × points per device must stay below 2^31 (shard the bases)");
     *window_bits = c;
     *windows = (256 + c - 1) / c;
     return 0;
@@ -739,7 +745,8 @@ int b200msm_table_build_device(int group, const void *d_bases, size_t n, int win
 int b200msm_run_table_device(int group, const void *d_table, size_t stride, int window_bits, const void *d_scalars, size_t n,
                              int mont, void *d_out, void *stream) {
     if (!d_out || (n && (!d_table || !d_scalars))) return fail(B200MSM_EINVAL, "null pointer");
-    if (window_bits < 2 || window_bits > 23 || n > stride) return fail(B200MSM_EINVAL, "bad table description");
+    if (window_bits < 2 || window_bits > 23 || n > stride || (uint64_t)stride * ((256 + window_bits - 1) / window_bits) >= (1ull << 31))
+        return fail(B200MSM_EINVAL, "bad table description");
     if (int rc = engine_init(-1, 1)) return rc;
     DeviceCtx *cx = ctx_for_current_device();
     if (!cx) return fail(B200MSM_EINVAL, "current device is not bound to the engine");
@@ -853,6 +860,11 @@ int b200msm_serialize(int group, const uint64_t *affine, size_t n, int compresse
 int b200msm_set_window_bits(int c) {
     if (c < 0 || c == 1 || c > 24) return fail(B200MSM_EINVAL, "window bits must be 0 (auto) or 2..24");
     g_eng.window_override = c;
+    return 0;
+}
+int b200msm_set_heavy_factor(int f) {
+    if (f < 0 || f > 1 << 20) return fail(B200MSM_EINVAL, "heavy factor must be 0 (automatic) or 1..2^20");
+    g_eng.heavy_factor = f;
     return 0;
 }
 int b200msm_set_glv(int mode) {

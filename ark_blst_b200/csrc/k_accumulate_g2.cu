@@ -10,23 +10,14 @@ void launch_accumulate_g2(const uint32_t *bases, const uint32_t *vals, const uin
 }
 void launch_heavy_g2(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
                      uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, void *hdr, void *hb, void *tasks,
-                     uint32_t *partials, uint32_t *buckets, int grid, cudaStream_t st, uint32_t nbw_tbl, size_t tbl_stride) {
+                     uint32_t *partials, uint32_t *buckets, int grid, cudaStream_t st) {
     count_launch();
     count_launch();
     count_launch();
-    k_plan_heavy<<<blocks_for(nb, 256), 256, 0, st>>>(start, order, nb, heavy_thr, HEAVY_CHUNK, nbw_tbl, (HeavyHeader *)hdr,
+    k_plan_heavy<<<blocks_for(nb, 256), 256, 0, st>>>(start, order, nb, heavy_thr, HEAVY_CHUNK, (HeavyHeader *)hdr,
                                                       (HeavyBucket *)hb, (HeavyTask *)tasks);
-    k_heavy_tasks<fp2, 128><<<grid, 128, 0, st>>>(bases, vals, (const HeavyHeader *)hdr, (const HeavyTask *)tasks, endo_x, n_pts, tbl_stride, partials);
-    k_heavy_final<fp2, 128><<<grid, 128, 0, st>>>((const HeavyHeader *)hdr, (const HeavyBucket *)hb, partials, buckets, nbw_tbl ? 1 : 0);
-}
-void launch_accumulate_tbl_g2(const uint32_t *table, size_t stride, const uint32_t *vals, const uint32_t *start,
-                              const uint32_t *order, uint32_t nbw, int nwin, uint32_t heavy_thr, uint32_t *buckets, cudaStream_t st) {
-    count_launch();
-    k_accumulate_tbl<fp2><<<blocks_for(nbw, 128), 128, 0, st>>>(table, stride, vals, start, order, nbw, nwin, heavy_thr, buckets);
-}
-void launch_heavy_fold_g2(const void *hdr, const void *hb, const uint32_t *sums, uint32_t nbw, uint32_t *buckets, cudaStream_t st) {
-    count_launch();
-    k_heavy_fold<fp2><<<8, 128, 0, st>>>((const HeavyHeader *)hdr, (const HeavyBucket *)hb, sums, nbw, buckets);
+    k_heavy_tasks<fp2, 128><<<grid, 128, 0, st>>>(bases, vals, (const HeavyHeader *)hdr, (const HeavyTask *)tasks, endo_x, n_pts, partials);
+    k_heavy_final<fp2, 128><<<grid, 128, 0, st>>>((const HeavyHeader *)hdr, (const HeavyBucket *)hb, partials, buckets);
 }
 void launch_table_shift_g2(const uint32_t *prev, size_t n, int c, uint32_t *jac_out, cudaStream_t st) {
     count_launch();

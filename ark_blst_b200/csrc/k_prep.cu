@@ -26,8 +26,8 @@ __global__ void k_digits_dbg(const uint32_t *__restrict__ scalars, size_t n, int
 // `glv` (G1 only): every scalar is split into (k1, k2) with k = k1 + k2·λ; entry i of a window is
 // k1's digit for point i, entry n + i is k2's digit for the endomorphism image φ(P_i).
 __global__ void __launch_bounds__(256)
-k_hist(const uint32_t *__restrict__ scalars, size_t n, int mont, int glv, int c, int nwin, uint32_t *__restrict__ dig,
-       uint32_t *__restrict__ count) {
+k_hist(const uint32_t *__restrict__ scalars, size_t n, int mont, int glv, int c, int nwin, int shared_buckets,
+       uint32_t *__restrict__ dig, uint32_t *__restrict__ count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8], s2[8];
@@ -47,7 +47,7 @@ k_hist(const uint32_t *__restrict__ scalars, size_t n, int mont, int glv, int c,
             uint32_t neg = d < 0;
             uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
             dig[(size_t)w * per_window + (half ? n : 0) + i] = (mag << 1) | neg;   // window-major; 0 = zero digit
-            if (mag) atomicAdd(&count[(uint32_t)w * nbw + (mag - 1)], 1u);
+            if (mag) atomicAdd(&count[(shared_buckets ? 0u : (uint32_t)w * nbw) + (mag - 1)], 1u);
         }
     }
 }
@@ -55,16 +55,18 @@ k_hist(const uint32_t *__restrict__ scalars, size_t n, int mont, int glv, int c,
 // scattered stores fall into one window's slice of vals (n·4 bytes) and its cursors — a working
 // set that stays in the 126 MB L2 up to n = 2^24 instead of spraying the whole n·W·4-byte array
 __global__ void __launch_bounds__(256)
-k_scatter(const uint32_t *__restrict__ dig, size_t n, int c, const uint32_t *__restrict__ start,
+k_scatter(const uint32_t *__restrict__ dig, size_t n, int c, size_t tbl_stride, const uint32_t *__restrict__ start,
           uint32_t *__restrict__ cursor, uint32_t *__restrict__ vals) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t w = blockIdx.y;
     uint32_t d = dig[(size_t)w * n + i];
     if (!d) return;
-    uint32_t bk = (w << (c - 1)) + ((d >> 1) - 1);
+    // table mode: one bucket set for all windows, the entry names table[w][i]. A bucket's cursor
+    // only moves forward, so the stores of one window pass still fall into one open sector per bucket.
+    uint32_t bk = (tbl_stride ? 0u : w << (c - 1)) + ((d >> 1) - 1);
     uint32_t pos = start[bk] + atomicAdd(&cursor[bk], 1u);
-    vals[pos] = (uint32_t)i | (d << 31);
+    vals[pos] = (uint32_t)(tbl_stride ? (size_t)w * tbl_stride + i : i) | (d << 31);
 }
 
 // exclusive scan of n u32 (n up to 2^27): 2048 elements per block, block sums scanned by one block
@@ -135,14 +137,8 @@ k_scan_add(uint32_t *__restrict__ out, size_t n, const uint32_t *__restrict__ ti
 
 // ---- buckets ordered by decreasing size: one counting-sort pass on min(count, SIZE_BINS-1) ------
 constexpr int SIZE_BINS = 4096, SIZE_THREADS = 256, SIZE_ITEMS = 4;
-// entries of bucket b; table mode: summed over the fold_n windows' segments
-__device__ __forceinline__ uint32_t bucket_size(const uint32_t *__restrict__ start, uint32_t b, uint32_t fold_stride, int fold_n) {
-    uint32_t cn = 0;
-    for (int w = 0; w < fold_n; w++) cn += start[(size_t)w * fold_stride + b + 1] - start[(size_t)w * fold_stride + b];
-    return cn;
-}
 __global__ void __launch_bounds__(SIZE_THREADS)
-k_size_hist(const uint32_t *__restrict__ start, uint32_t nb, uint32_t fold_stride, int fold_n, uint32_t *__restrict__ hist) {
+k_size_hist(const uint32_t *__restrict__ start, uint32_t nb, uint32_t *__restrict__ hist) {
     __shared__ uint32_t lh[SIZE_BINS];
     for (int k = threadIdx.x; k < SIZE_BINS; k += SIZE_THREADS) lh[k] = 0;
     __syncthreads();
@@ -151,7 +147,7 @@ k_size_hist(const uint32_t *__restrict__ start, uint32_t nb, uint32_t fold_strid
     for (int k = 0; k < SIZE_ITEMS; k++) {
         uint32_t b = b0 + k;
         if (b < nb) {
-            uint32_t cn = bucket_size(start, b, fold_stride, fold_n);
+            uint32_t cn = start[b + 1] - start[b];
             atomicAdd(&lh[cn < SIZE_BINS - 1 ? cn : SIZE_BINS - 1], 1u);
         }
     }
@@ -172,8 +168,8 @@ k_size_scan(const uint32_t *__restrict__ hist, uint32_t *__restrict__ binstart) 
     }
 }
 __global__ void __launch_bounds__(SIZE_THREADS)
-k_size_scatter(const uint32_t *__restrict__ start, uint32_t nb, uint32_t fold_stride, int fold_n,
-               uint32_t *__restrict__ bincursor, uint32_t *__restrict__ order) {
+k_size_scatter(const uint32_t *__restrict__ start, uint32_t nb, uint32_t *__restrict__ bincursor,
+               uint32_t *__restrict__ order) {
     __shared__ uint32_t lh[SIZE_BINS];   // local count, then global base of this block's run per bin
     for (int k = threadIdx.x; k < SIZE_BINS; k += SIZE_THREADS) lh[k] = 0;
     __syncthreads();
@@ -184,7 +180,7 @@ k_size_scatter(const uint32_t *__restrict__ start, uint32_t nb, uint32_t fold_st
         uint32_t b = b0 + k;
         bin[k] = 0xffffffffu;
         if (b < nb) {
-            uint32_t cn = bucket_size(start, b, fold_stride, fold_n);
+            uint32_t cn = start[b + 1] - start[b];
             bin[k] = cn < SIZE_BINS - 1 ? cn : SIZE_BINS - 1;
             rank[k] = atomicAdd(&lh[bin[k]], 1u);
         }
@@ -199,27 +195,27 @@ k_size_scatter(const uint32_t *__restrict__ start, uint32_t nb, uint32_t fold_st
 }
 
 void launch_group_by_bucket(const uint32_t *scalars, size_t n, int mont, int glv, int c, int nwin, uint32_t nb, uint32_t *dig,
-                            uint32_t *count, uint32_t *start, uint32_t *tile_sums, uint32_t *vals, cudaStream_t st) {
+                            uint32_t *count, uint32_t *start, uint32_t *tile_sums, uint32_t *vals, cudaStream_t st,
+                            size_t tbl_stride) {
     for (int k = 0; k < 7; k++) count_launch();
     cudaMemsetAsync(count, 0, (size_t)nb * 4, st);
-    k_hist<<<blocks_for(n, 256), 256, 0, st>>>(scalars, n, mont, glv, c, nwin, dig, count);
+    k_hist<<<blocks_for(n, 256), 256, 0, st>>>(scalars, n, mont, glv, c, nwin, tbl_stride ? 1 : 0, dig, count);
     size_t ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
     k_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(count, start, nb, tile_sums);
     k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, ntiles, tile_sums + ntiles);
     k_scan_add<<<blocks_for(nb, 256), 256, 0, st>>>(start, nb, tile_sums, tile_sums + ntiles);
     cudaMemsetAsync(count, 0, (size_t)nb * 4, st);   // reused as the scatter cursors
     const size_t entries = glv ? 2 * n : n;  // per window
-    k_scatter<<<dim3(blocks_for(entries, 256), (unsigned)nwin), 256, 0, st>>>(dig, entries, c, start, count, vals);
+    k_scatter<<<dim3(blocks_for(entries, 256), (unsigned)nwin), 256, 0, st>>>(dig, entries, c, tbl_stride, start, count, vals);
 }
 // hist: 2·SIZE_BINS u32 of scratch
-void launch_order_by_size(const uint32_t *start, uint32_t nb, uint32_t *hist, uint32_t *order, cudaStream_t st,
-                          uint32_t fold_stride, int fold_n) {
+void launch_order_by_size(const uint32_t *start, uint32_t nb, uint32_t *hist, uint32_t *order, cudaStream_t st) {
     for (int k = 0; k < 3; k++) count_launch();
     cudaMemsetAsync(hist, 0, SIZE_BINS * 4, st);
     unsigned blocks = blocks_for(nb, SIZE_THREADS * SIZE_ITEMS);
-    k_size_hist<<<blocks, SIZE_THREADS, 0, st>>>(start, nb, fold_stride, fold_n, hist);
+    k_size_hist<<<blocks, SIZE_THREADS, 0, st>>>(start, nb, hist);
     k_size_scan<<<1, SCAN_THREADS, 0, st>>>(hist, hist + SIZE_BINS);
-    k_size_scatter<<<blocks, SIZE_THREADS, 0, st>>>(start, nb, fold_stride, fold_n, hist + SIZE_BINS, order);
+    k_size_scatter<<<blocks, SIZE_THREADS, 0, st>>>(start, nb, hist + SIZE_BINS, order);
 }
 
 void launch_digits_dbg(const uint32_t *scalars, size_t n, int mont, int c, int nwin, int *out, cudaStream_t st) {

@@ -12,12 +12,13 @@ namespace b200msm {
 void launch_digits_dbg(const uint32_t *scalars, size_t n, int mont, int c, int nwin, int *out, cudaStream_t st);
 // hand-written grouping by bucket (counting sort on the bucket id, built from the scalars):
 // glv: split every scalar in two 128-bit halves (entries per window double); dig: entries·nwin u32, count: nb u32, start: nb+2 u32, tile_sums: nb/2048+2 u32, vals: ≥ n·nwin u32
+// tbl_stride > 0 (fixed-base window table, `tbl_stride` points per window): all windows share one bucket set — nb = 2^(c−1),
+// entries are grouped by the digit alone and carry the table index w·tbl_stride + i (must stay below 2^31)
 void launch_group_by_bucket(const uint32_t *scalars, size_t n, int mont, int glv, int c, int nwin, uint32_t nb, uint32_t *dig,
-                            uint32_t *count, uint32_t *start, uint32_t *tile_sums, uint32_t *vals, cudaStream_t st);
+                            uint32_t *count, uint32_t *start, uint32_t *tile_sums, uint32_t *vals, cudaStream_t st,
+                            size_t tbl_stride = 0);
 // bucket ids in decreasing-size order (counting sort on the clamped size); hist: 8192 u32 scratch
-// fold_n > 1 (table mode): nb buckets whose size is summed over fold_n windows, fold_stride buckets apart
-void launch_order_by_size(const uint32_t *start, uint32_t nb, uint32_t *hist, uint32_t *order, cudaStream_t st,
-                          uint32_t fold_stride = 0, int fold_n = 1);
+void launch_order_by_size(const uint32_t *start, uint32_t nb, uint32_t *hist, uint32_t *order, cudaStream_t st);
 // k_accumulate_g{1,2}.cu
 constexpr uint32_t HEAVY_CHUNK = 4096;  // entries per block task of a heavy bucket
 // endo_x / n_pts: GLV (G1): value indices ≥ n_pts name φ(P) = (β·x, y) of point index − n_pts, x read from
@@ -30,20 +31,10 @@ void launch_endo_table_g1(const uint32_t *bases, size_t n, uint32_t *endo_x, cud
 // plan + block tasks + per-bucket fold for buckets above heavy_thr; hdr must be zeroed (8 bytes)
 void launch_heavy_g1(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
                      uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, void *hdr, void *hb, void *tasks,
-                     uint32_t *partials, uint32_t *buckets, int grid, cudaStream_t st, uint32_t nbw_tbl = 0, size_t tbl_stride = 0);
+                     uint32_t *partials, uint32_t *buckets, int grid, cudaStream_t st);
 void launch_heavy_g2(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
                      uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, void *hdr, void *hb, void *tasks,
-                     uint32_t *partials, uint32_t *buckets, int grid, cudaStream_t st, uint32_t nbw_tbl = 0, size_t tbl_stride = 0);
-// fixed-base window table (table[w][i] = 2^(c·w)·P_i, affine, `stride` points per window): one bucket set for all
-// windows. `order` ranks the nbw buckets by size summed over the windows; launch_heavy_* runs with order = nullptr,
-// nb = all (window, bucket) segments, nbw_tbl = nbw, tbl_stride = stride and `buckets` = a per-slot sum array, which
-// launch_heavy_fold_* then adds into the shared buckets.
-void launch_accumulate_tbl_g1(const uint32_t *table, size_t stride, const uint32_t *vals, const uint32_t *start,
-                              const uint32_t *order, uint32_t nbw, int nwin, uint32_t heavy_thr, uint32_t *buckets, cudaStream_t st);
-void launch_accumulate_tbl_g2(const uint32_t *table, size_t stride, const uint32_t *vals, const uint32_t *start,
-                              const uint32_t *order, uint32_t nbw, int nwin, uint32_t heavy_thr, uint32_t *buckets, cudaStream_t st);
-void launch_heavy_fold_g1(const void *hdr, const void *hb, const uint32_t *sums, uint32_t nbw, uint32_t *buckets, cudaStream_t st);
-void launch_heavy_fold_g2(const void *hdr, const void *hb, const uint32_t *sums, uint32_t nbw, uint32_t *buckets, cudaStream_t st);
+                     uint32_t *partials, uint32_t *buckets, int grid, cudaStream_t st);
 // jac_out[i] = 2^c · prev[i] (affine in, Jacobian out): one window step of the table build
 void launch_table_shift_g1(const uint32_t *prev, size_t n, int c, uint32_t *jac_out, cudaStream_t st);
 void launch_table_shift_g2(const uint32_t *prev, size_t n, int c, uint32_t *jac_out, cudaStream_t st);

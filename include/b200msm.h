@@ -136,6 +136,10 @@ int b200msm_set_window_bits(int c);
 /* G1 only: GLV split of every scalar into two 128-bit halves over (P, φ(P)) — halves the windows
  * of the on-device Horner chain. -1 = automatic (time model), 0 = never, 1 = always. */
 int b200msm_set_glv(int mode);
+/* Buckets holding more than max(32, factor × mean occupancy, entries/175000) entries leave the
+ * one-thread-per-bucket kernel for the block-cooperative path (0 = automatic: 3, or 4 with a
+ * fixed-base table). */
+int b200msm_set_heavy_factor(int factor);
 /* Large inputs are cut into passes automatically (sort arrays < 2^32 entries, scratch within the
  * free HBM) — the chunking the reference left as a TODO (src/gpu.rs:238-239). A non-zero value
  * forces at most that many points per pass (tests); 0 = automatic. */

@@ -94,9 +94,8 @@ def test_table_edge_scalars(eng, g2):
 
 
 def test_table_witness_like_scalars(eng, cref):
-    """≈40 % zeros, ≈20 % ones, ≈10 % small: the digit-1 segment of window 0 goes down the
-    block-cooperative path and is folded into the shared bucket afterwards; a second heavy
-    segment that shares its bucket (scalars 2^c → window 1, bucket 1) exercises the fold's merge"""
+    """≈30 % zeros, ≈20 % ones, ≈15 % 2^c, ≈10 % small: bucket 1 collects window 0's ones and
+    window 1's 2^c entries and goes down the block-cooperative heavy path"""
     n, c = 1 << 13, 12
     rng = random.Random(6)
     bases = cref.synth_bases(0, 56, n)

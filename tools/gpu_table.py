@@ -11,6 +11,8 @@ from bench import work_model, FPMUL_IMAD
 
 L = eng._lib.lib
 L.b200msm_set_profiling(1)
+import os
+if os.environ.get("TBL_HEAVY"): L.b200msm_set_heavy_factor(int(os.environ["TBL_HEAVY"]))
 peak = eng.imad_peak()["imad_per_s"]
 st = torch.cuda.current_stream().cuda_stream
 
