@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200msm.so")
+# B200MSM_LIB: another build of the same library (A/B experiments with kernel variants); still no fallback
+LIB_PATH = os.environ.get("B200MSM_LIB") or os.path.join(_HERE, "libb200msm.so")
 
 u64p = ctypes.POINTER(ctypes.c_uint64)
 i32p = ctypes.POINTER(ctypes.c_int32)

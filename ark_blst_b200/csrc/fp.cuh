@@ -165,6 +165,9 @@ __device__ __forceinline__ void fp_mul(fp &r, const fp &a, const fp &b) {
     for (int i = 0; i < 12; i++) r.l[i] = even[i];
 }
 
+// (A shared out-of-line copy of the product, called with operands in registers, shrinks the
+// accumulation loop from ≈117 KB to ≈40 KB of SASS but measured 1–5 % SLOWER on B200: the ≈40
+// register moves per call cost more than the instruction-cache pressure they remove.)
 // Squaring reuses the product. A dedicated squaring (66 off-diagonal + 12 diagonal products, 222
 // instead of 288 fused IMAD.WIDE) was measured on B200 and is SLOWER inside the accumulation
 // kernel (6.24 ms vs 6.13 ms at n = 2^20): it trades 66 fmaheavy issues for ~190 serial
