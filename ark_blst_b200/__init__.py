@@ -12,6 +12,7 @@ from .msm import (  # noqa: F401
     ResidentBases,
     imad_peak,
     last_phase_ms,
+    last_plan,
     run_device,
     run_table_device,
     table_build_device,

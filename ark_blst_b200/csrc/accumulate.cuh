@@ -94,18 +94,35 @@ k_table_shift(const uint32_t *__restrict__ prev, size_t n, int c, uint32_t *__re
     jac_store(jac_out + i * (3 * W), r);
 }
 
-// β·x for every base (G1 GLV): one product per point, written as a dense n×48-byte table
+// β·x for every base (GLV): the x coordinates of the endomorphism images φ(P) = (β·x, y) = λ·P, written as a
+// dense table of field elements. β is the cube root of unity in Fp that makes φ act as THE λ of
+// scalar.cuh's decomposition: β on G1 and β² on G2 (checked against the big-int oracle: λ·Q = (β²·x, y)
+// for Q in G2). Fp2 coordinates take β on both components. Montgomery limbs.
 __device__ __constant__ const uint32_t GLV_BETA[12] = {0x8671f071, 0xcd03c9e4, 0x1fcda5d2, 0x5dab2246, 0xd3851b95, 0x587042af,
                                                        0x01bacb9e, 0x8eb60ebe, 0x83d050d2, 0x03f97d6e, 0x54638741, 0x18f02065};
+__device__ __constant__ const uint32_t GLV_BETA_SQ[12] = {0x798a64e8, 0x30f1361b, 0x7ece5a2a, 0xf3b8ddab, 0xc61577f7, 0x16a8ca3a,
+                                                          0x74fd029b, 0xc26a2ff8, 0x60701c6e, 0x3636b766, 0x241b6160, 0x051ba4ab};
+__device__ __forceinline__ void endo_mul(fp &r, const fp &x) {
+    fp beta;
+    fp_load(beta, GLV_BETA);
+    fp_mul(r, x, beta);
+}
+__device__ __forceinline__ void endo_mul(fp2 &r, const fp2 &x) {
+    fp beta;
+    fp_load(beta, GLV_BETA_SQ);
+    fp_mul(r.c0, x.c0, beta);
+    fp_mul(r.c1, x.c1, beta);
+}
+template <class F>
 static __global__ void __launch_bounds__(256)
 k_endo_table(const uint32_t *__restrict__ bases, size_t n, uint32_t *__restrict__ endo_x) {
+    constexpr int W = field_words<F>::value;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fp x, beta;
-    fp_load(x, bases + i * 24);
-    fp_load(beta, GLV_BETA);
-    fp_mul(x, x, beta);
-    fp_store(endo_x + i * 12, x);
+    F x;
+    f_load(x, bases + i * (2 * W));
+    endo_mul(x, x);
+    f_store(endo_x + i * W, x);
 }
 
 // ---- heavy buckets ---------------------------------------------------------------------------

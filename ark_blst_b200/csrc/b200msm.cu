@@ -67,9 +67,19 @@ struct DevBuf {
 
 struct Plan {
     int c = 0, nwin = 0;
-    bool glv = false;          // G1: split every scalar into two 128-bit halves (k1 + k2·λ)
+    bool glv = false;          // split every scalar into two 128-bit halves (k1 + k2·λ) over P and φ(P) = (β·x, y)
+    bool split = false;        // GLV with c | 128: unsigned top digit spread over the last two windows (k_hist)
     uint32_t nbw = 0, nb = 0;  // buckets per window, total
 };
+
+// Windows of a plan. Plain: c·W ≥ 256 so the top Booth carry stays inside. GLV halves are below
+// 2^128: when c divides 128 their top c bits are taken unsigned (digit ≤ 2^c → two windows' worth
+// of buckets, no carry window); otherwise c·W ≥ 129 as for the plain plan.
+int plan_windows(bool glv, int c, bool *split) {
+    *split = glv && 128 % c == 0;
+    if (!glv) return (256 + c - 1) / c;
+    return *split ? 128 / c + 1 : (129 + c - 1) / c;
+}
 
 // Window width and GLV choice from a time model fitted to the measured phases on B200 (µs):
 // accumulation at 88 % (G1) / 76 % (G2) of the 18.5 T IMAD/s pipe, the fan-in-32 reduction level
@@ -77,20 +87,38 @@ struct Plan {
 // entry.  Without GLV this lands on the work-minimising c* of SURVEY §8(d) (13/16/18/20 at
 // 2^16/20/22/24) — the width the roofline numerator assumes.
 double plan_time_us(size_t n, bool g2, bool glv, int c) {
-    const double bits = glv ? 129 : 256, W = std::ceil(bits / c), entries = (glv ? 2.0 : 1.0) * (double)n;
+    bool split;
+    const double W = plan_windows(glv, c, &split), entries = (glv ? 2.0 : 1.0) * (double)n;
+    const double Wacc = split ? W - 1 : W;  // an entry lands in one of the two top windows
     const double madd = g2 ? 28 : 10, add = g2 ? 40 : 14, pipe = 18.5e6;  // IMAD per µs
-    double t = entries * W * madd * 588 / (pipe * (g2 ? 0.76 : 0.88));
+    // one thread per bucket: below ≈2.5 warps per scheduler (4 × 148 of them) the dependent-issue latency of the
+    // product chain shows (measured with 2^15 buckets: 0.6 of the pipe)
+    // (GLV: the φ(P) entries read x from the β·x table and y from the base record — measured 2.5 % / 6 % slower)
+    const double wps = W * std::pow(2.0, c - 1) / 32 / 592;
+    const double eff = std::min(g2 ? 0.76 : 0.88, 0.35 * wps) * (glv ? (g2 ? 0.94 : 0.975) : 1.0);
+    double t = entries * Wacc * madd * 588 / (pipe * eff);
     t += W * std::pow(2.0, c - 1) * 2 * add * 588 / (pipe * 0.55);
-    t += W * c * (g2 ? 11.0 : 3.4) + 250;
+    t += (split ? (W - 2) * c + c - 1 : (W - 1) * c) * (g2 ? 11.0 : 3.4) + 250;
     t += entries * W * 2.3e-5;
-    if (glv) t += (double)n * 588 / (pipe * 0.5);
+    if (glv) {
+        t += (double)n * (g2 ? 2 : 1) * 588 / (pipe * 0.5) + (double)n * 4e-5;  // β·x table, decomposition
+        // a top window with few bits piles its entries into few buckets: block-cooperative path, ≈3.5× the cost
+        // The halves are below λ ≈ 0.673·2^128, so the top window only uses ⌊λ / 2^(c(W−1))⌋ + 1 of its buckets.
+        // When that is few, its entries pile up past the heavy-bucket threshold and go down the block-cooperative
+        // path (and serialise the grouping's atomics): never pick such a width.
+        const int shift = c * ((int)W - 1);
+        const double top_buckets = std::floor(0.673 * std::pow(2.0, 128 - shift)) + 1;
+        const double thr = std::max(std::max(32.0, 3 * entries / std::pow(2.0, c - 1)), entries * W / 175000);
+        if (!split && entries / top_buckets > 0.7 * thr) t += 1e5;
+    }
     return t;
 }
 void auto_plan(size_t n, bool g2, int glv_mode, int c_override, Plan &pl) {
     double best = 1e300;
-    for (int glv = 0; glv <= (g2 ? 0 : 1); glv++) {
+    for (int glv = 0; glv <= 1; glv++) {
         if (glv_mode == 0 && glv) continue;
-        if (glv_mode == 1 && !glv && !g2) continue;
+        if (glv_mode == 1 && !glv) continue;
+        if (glv && glv_mode < 0 && n > (1u << 22)) continue;  // automatic choice only where it was measured to pay
         if (glv && 2 * n >= (1ull << 31)) continue;
         for (int c = 2; c <= 22; c++) {
             if (c_override > 0 && c != c_override) continue;
@@ -98,10 +126,16 @@ void auto_plan(size_t n, bool g2, int glv_mode, int c_override, Plan &pl) {
             if (t < best) { best = t; pl.c = c; pl.glv = glv; }
         }
     }
-    pl.nwin = ((pl.glv ? 129 : 256) + pl.c - 1) / pl.c;  // c·W ≥ bits + 1: the top Booth carry stays inside
+    pl.nwin = plan_windows(pl.glv, pl.c, &pl.split);
     pl.nbw = 1u << (pl.c - 1);
     pl.nb = pl.nbw * (uint32_t)pl.nwin;
 }
+int auto_window(size_t n, bool g2) {  // non-GLV width (scratch estimates)
+    Plan pl;
+    auto_plan(n, g2, 0, 0, pl);
+    return pl.c;
+}
+
 // Fixed-base window table (table[w][i] = 2^(c·w)·P_i): one bucket set for all windows, no Horner
 // chain, so the width only trades the n·W additions of the accumulation against one window's
 // bucket reduction (+ a log-depth tree) — wider than the plain plan's at every n.
@@ -116,21 +150,20 @@ int table_plan(size_t n, bool g2) {
     int bc = 10;
     for (int c = 10; c <= 23; c++) {           // W ≤ 26: the table stays within 26× the bases
         const double W = std::ceil(256.0 / c);
-        double t = (double)n * W * madd * 588 / (pipe * (g2 ? 0.76 : 0.88)) + std::pow(2.0, c - 1) * 2 * add * 588 / (pipe * 0.55) +
+        // one thread per bucket and only 2^(c−1) buckets in all: below ≈2.5 warps per scheduler (4 × 148 of them)
+        // the dependent-issue latency of the product chain shows (measured: c = 16 → 0.6 of the pipe)
+        const double wps = std::pow(2.0, c - 1) / 32 / 592, eff = std::min(g2 ? 0.76 : 0.88, 0.35 * wps);
+        double t = (double)n * W * madd * 588 / (pipe * eff) + std::pow(2.0, c - 1) * 2 * add * 588 / (pipe * 0.55) +
                    (double)n * W * 2.3e-5 + c * (g2 ? 40.0 : 16.0);
         // the top window only holds 255 − (W−1)·c bits: when that is few, its n entries pile into a
         // handful of buckets and go down the block-cooperative path (≈3.5× the cost per entry)
         const int topbits = std::max(0, 255 - ((int)W - 1) * c);
         const double m = (double)n * W, thr = std::max(std::max(32.0, 4 * m / std::pow(2.0, c - 1)), m / 175000);
         if (topbits < c - 1 && (double)n / std::pow(2.0, topbits) > thr) t += (double)n * madd * 588 / pipe * 3.5;
+        if (topbits < c - 5) t += 1e4;  // … and their counters serialise the grouping's atomics: never pick such a width
         if (t < best) { best = t; bc = c; }
     }
     return bc;
-}
-int auto_window(size_t n, bool g2) {  // non-GLV width (scratch estimates)
-    Plan pl;
-    auto_plan(n, g2, 0, 0, pl);
-    return pl.c;
 }
 
 struct DeviceCtx {
@@ -146,6 +179,7 @@ struct DeviceCtx {
     DevBuf hvy_hdr, hvy_buckets, hvy_tasks, hvy_partials, treeS[2], treeV[2], treeC[2], wsum, chunk_partials, norm_in, norm_out, tile_sums, size_hist, endo, tbl_tmp;
     cudaEvent_t ev[8] = {};
     double phase_ms[8] = {};
+    int last_plan[4] = {0, 0, 0, 0};  // c, windows, GLV (0/1/2 = off / on / on with the unsigned top digit), table
     bool phase_pending = false;
     int sm_count = 0;
     std::vector<DevBuf *> scratch() {
@@ -171,7 +205,7 @@ struct Engine {
     std::vector<std::unique_ptr<DeviceCtx>> ctx;
     int window_override = 0;
     size_t max_chunk_override = 0;
-    int glv_mode = 0;   // -1 automatic (time model), 0 never (default: measured slower, see profiles/r01_experiments.md), 1 always (G1 only)
+    int glv_mode = -1;  // -1 automatic (time model; default), 0 never, 1 always
     bool profiling = false;
     int heavy_factor = 0;  // a bucket is heavy above heavy_factor × the mean occupancy (see run_pass); 0 = automatic
 };
@@ -245,12 +279,13 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     if (tbl) {  // the table fixes the width
         pl.c = tbl->c;
         pl.nwin = tbl->nwin;
-        pl.glv = false;
+        pl.glv = pl.split = false;
         pl.nbw = 1u << (pl.c - 1);
         pl.nb = pl.nbw;                       // one bucket set shared by all windows
         d_bases = (const uint32_t *)tbl->p;
     } else auto_plan(n, g2, g_eng.glv_mode, std::min(g_eng.window_override, 22), pl);
     const int rwin = tbl ? 1 : pl.nwin;       // windows the reduction sees
+    cx.last_plan[0] = pl.c; cx.last_plan[1] = pl.nwin; cx.last_plan[2] = pl.glv ? (pl.split ? 2 : 1) : 0; cx.last_plan[3] = tbl ? 1 : 0;
     const size_t entries = pl.glv ? 2 * n : n;  // per window
     const size_t m = entries * (size_t)pl.nwin;
     const bool prof = g_eng.profiling;
@@ -291,7 +326,7 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     mark();
     // 1+2. canonical scalars → window digits, per-bucket histogram, scan → bucket offsets, scatter
     //      of the point indices (a counting sort on the bucket id; zero digits are dropped)
-    launch_group_by_bucket(d_scalars, n, mont, pl.glv ? 1 : 0, pl.c, pl.nwin, pl.nb, cx.digits.as<uint32_t>(), cx.cnt.as<uint32_t>(), start,
+    launch_group_by_bucket(d_scalars, n, mont, pl.glv ? (pl.split ? 2 : 1) : 0, pl.c, pl.nwin, pl.nb, cx.digits.as<uint32_t>(), cx.cnt.as<uint32_t>(), start,
                            cx.tile_sums.as<uint32_t>(), vals, st, tbl ? tbl->stride : 0);
     mark();
     mark();
@@ -304,8 +339,8 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     const uint32_t *endo_x = nullptr;
     uint32_t n_pts = 0xffffffffu;
     if (pl.glv) {  // β·x table for the endomorphism images (one product per base)
-        if (int rc = cx.endo.reserve(n * 48)) return rc;
-        launch_endo_table_g1(d_bases, n, cx.endo.as<uint32_t>(), st);
+        if (int rc = cx.endo.reserve(n * (size_t)W * 4)) return rc;
+        (g2 ? launch_endo_table_g2 : launch_endo_table_g1)(d_bases, n, cx.endo.as<uint32_t>(), st);
         endo_x = cx.endo.as<uint32_t>();
         n_pts = (uint32_t)n;
     }
@@ -362,7 +397,7 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     mark();
     // 6. window values and Horner over the windows → one Jacobian point
     (g2 ? launch_combine_g2 : launch_combine_g1)(Sin, cx.treeV[cur].as<uint32_t>(), Cin ? Ccur : nullptr, tstride, logS, log2M,
-                                                 rwin, pl.c, cx.wsum.as<uint32_t>(), d_out, st);
+                                                 rwin, pl.c, pl.split ? 1 : 0, cx.wsum.as<uint32_t>(), d_out, st);
     mark();
     CUDA_TRY(cudaGetLastError());
     cx.phase_pending = prof;  // elapsed times are read lazily by b200msm_last_phase_ms (no sync here)
@@ -376,7 +411,7 @@ size_t pass_scratch_bytes(size_t n, bool g2, int c_override, bool table = false)
     size_t nwin = (256 + c - 1) / c, nb = nwin << (c - 1), m = n * nwin;  // the GLV plan needs about the same
     size_t PB = g2 ? 384 : 192;
     if (table) return m * 8 + (nb / nwin) * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + (64u << 20);
-    return m * 8 + nb * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + n * 48 + (64u << 20);
+    return m * 8 + nb * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + n * (PB / 4) + (64u << 20);
 }
 
 // The whole MSM on one device: one pass when it fits, otherwise the chunking the reference left
@@ -878,6 +913,14 @@ int b200msm_set_max_chunk(size_t max_points_per_pass) {
 }
 int b200msm_set_profiling(int on) {
     g_eng.profiling = on != 0;
+    return 0;
+}
+int b200msm_last_plan(int out[4]) {
+    if (!g_eng.inited) return fail(B200MSM_EINVAL, "engine not initialised");
+    DeviceCtx *cx = ctx_for_current_device();
+    if (!cx) cx = g_eng.ctx[0].get();
+    std::lock_guard<std::mutex> lk(cx->mu);
+    memcpy(out, cx->last_plan, sizeof cx->last_plan);
     return 0;
 }
 int b200msm_last_phase_ms(double out[8]) {

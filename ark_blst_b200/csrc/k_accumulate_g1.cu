@@ -21,7 +21,7 @@ void launch_heavy_g1(const uint32_t *bases, const uint32_t *vals, const uint32_t
 }
 void launch_endo_table_g1(const uint32_t *bases, size_t n, uint32_t *endo_x, cudaStream_t st) {
     count_launch();
-    k_endo_table<<<blocks_for(n, 256), 256, 0, st>>>(bases, n, endo_x);
+    k_endo_table<fp><<<blocks_for(n, 256), 256, 0, st>>>(bases, n, endo_x);
 }
 void launch_table_shift_g1(const uint32_t *prev, size_t n, int c, uint32_t *jac_out, cudaStream_t st) {
     count_launch();

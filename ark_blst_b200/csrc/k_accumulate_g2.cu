@@ -19,6 +19,10 @@ void launch_heavy_g2(const uint32_t *bases, const uint32_t *vals, const uint32_t
     k_heavy_tasks<fp2, 128><<<grid, 128, 0, st>>>(bases, vals, (const HeavyHeader *)hdr, (const HeavyTask *)tasks, endo_x, n_pts, partials);
     k_heavy_final<fp2, 128><<<grid, 128, 0, st>>>((const HeavyHeader *)hdr, (const HeavyBucket *)hb, partials, buckets);
 }
+void launch_endo_table_g2(const uint32_t *bases, size_t n, uint32_t *endo_x, cudaStream_t st) {
+    count_launch();
+    k_endo_table<fp2><<<blocks_for(n, 256), 256, 0, st>>>(bases, n, endo_x);
+}
 void launch_table_shift_g2(const uint32_t *prev, size_t n, int c, uint32_t *jac_out, cudaStream_t st) {
     count_launch();
     k_table_shift<fp2><<<blocks_for(n, 128), 128, 0, st>>>(prev, n, c, jac_out);

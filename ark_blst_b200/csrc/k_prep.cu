@@ -40,10 +40,21 @@ k_hist(const uint32_t *__restrict__ scalars, size_t n, int mont, int glv, int c,
     }
     const uint32_t nbw = 1u << (c - 1);
     const size_t per_window = glv ? 2 * n : n;
-    for (int half = 0; half <= glv; half++) {
+    // glv == 2 (c divides 128): the top c bits of a 128-bit half are taken UNSIGNED, so no carry
+    // window follows them; their digit u ∈ [0, 2^c] goes to window nwin−2 when u ≤ 2^(c−1) and, as
+    // u − 2^(c−1), to window nwin−1 otherwise (k_combine adds 2^(c−1)·Σ buckets for that window
+    // and gives both the weight of window nwin−2)
+    const int split = glv == 2;
+    for (int half = 0; half <= (glv ? 1 : 0); half++) {
         const uint32_t *sc = half ? s2 : s;
+        uint32_t utop = 0;
+        if (split) utop = scalar_bits(sc, (nwin - 2) * c - 1, c + 1), utop = (utop >> 1) + (utop & 1);
         for (int w = 0; w < nwin; w++) {
-            int d = booth_digit(sc, w, c);
+            int d;
+            if (split && w >= nwin - 2) {
+                const uint32_t hi = utop > nbw;
+                d = w == nwin - 2 ? (hi ? 0 : (int)utop) : (hi ? (int)(utop - nbw) : 0);
+            } else d = booth_digit(sc, w, c);
             uint32_t neg = d < 0;
             uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
             dig[(size_t)w * per_window + (half ? n : 0) + i] = (mag << 1) | neg;   // window-major; 0 = zero digit

@@ -18,9 +18,9 @@ void launch_tree_level_g2(const uint32_t *Sin, size_t sin_stride, const uint32_t
                                                                  out_stride, S, j, nwin);
 }
 void launch_combine_g2(const uint32_t *Sroot, const uint32_t *V, const uint32_t *Croot, size_t stride, int logS, int log2M,
-                       int nwin, int c, uint32_t *wsum, uint32_t *out, cudaStream_t st) {
+                       int nwin, int c, int split_top, uint32_t *wsum, uint32_t *out, cudaStream_t st) {
     count_launch();
-    k_combine<fp2><<<1, 128, 0, st>>>(Sroot, V, Croot, stride, logS, log2M, nwin, c, wsum, out);
+    k_combine<fp2><<<1, 128, 0, st>>>(Sroot, V, Croot, stride, logS, log2M, nwin, c, split_top, wsum, out);
 }
 void launch_sum_partials_g2(const uint32_t *partials, int count, uint32_t *out, cudaStream_t st) {
     count_launch();

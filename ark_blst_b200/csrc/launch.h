@@ -11,7 +11,8 @@ namespace b200msm {
 // k_prep.cu
 void launch_digits_dbg(const uint32_t *scalars, size_t n, int mont, int c, int nwin, int *out, cudaStream_t st);
 // hand-written grouping by bucket (counting sort on the bucket id, built from the scalars):
-// glv: split every scalar in two 128-bit halves (entries per window double); dig: entries·nwin u32, count: nb u32, start: nb+2 u32, tile_sums: nb/2048+2 u32, vals: ≥ n·nwin u32
+// glv: 1 = split every scalar in two 128-bit halves (entries per window double), 2 = the same with the top c bits taken
+// unsigned and spread over the last two windows (c | 128, nwin = 128/c + 1; see k_hist); dig: entries·nwin u32, count: nb u32, start: nb+2 u32, tile_sums: nb/2048+2 u32, vals: ≥ n·nwin u32
 // tbl_stride > 0 (fixed-base window table, `tbl_stride` points per window): all windows share one bucket set — nb = 2^(c−1),
 // entries are grouped by the digit alone and carry the table index w·tbl_stride + i (must stay below 2^31)
 void launch_group_by_bucket(const uint32_t *scalars, size_t n, int mont, int glv, int c, int nwin, uint32_t nb, uint32_t *dig,
@@ -21,13 +22,14 @@ void launch_group_by_bucket(const uint32_t *scalars, size_t n, int mont, int glv
 void launch_order_by_size(const uint32_t *start, uint32_t nb, uint32_t *hist, uint32_t *order, cudaStream_t st);
 // k_accumulate_g{1,2}.cu
 constexpr uint32_t HEAVY_CHUNK = 4096;  // entries per block task of a heavy bucket
-// endo_x / n_pts: GLV (G1): value indices ≥ n_pts name φ(P) = (β·x, y) of point index − n_pts, x read from
+// endo_x / n_pts: GLV: value indices ≥ n_pts name φ(P) = (β·x, y) of point index − n_pts, x read from
 // the β·x table; pass nullptr / 0xffffffff when unused
 void launch_accumulate_g1(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
                           uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, uint32_t *buckets, cudaStream_t st);
 void launch_accumulate_g2(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
                           uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, uint32_t *buckets, cudaStream_t st);
 void launch_endo_table_g1(const uint32_t *bases, size_t n, uint32_t *endo_x, cudaStream_t st);
+void launch_endo_table_g2(const uint32_t *bases, size_t n, uint32_t *endo_x, cudaStream_t st);
 // plan + block tasks + per-bucket fold for buckets above heavy_thr; hdr must be zeroed (8 bytes)
 void launch_heavy_g1(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
                      uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, void *hdr, void *hb, void *tasks,
@@ -52,9 +54,9 @@ void launch_tree_level_g2(const uint32_t *Sin, size_t sin_stride, const uint32_t
                           uint32_t *Sout, uint32_t *Vout, uint32_t *Cout, size_t out_stride, uint32_t S, int j, uint32_t nwin,
                           cudaStream_t st);
 void launch_combine_g1(const uint32_t *Sroot, const uint32_t *V, const uint32_t *Croot, size_t stride, int logS, int log2M,
-                       int nwin, int c, uint32_t *wsum, uint32_t *out, cudaStream_t st);
+                       int nwin, int c, int split_top, uint32_t *wsum, uint32_t *out, cudaStream_t st);
 void launch_combine_g2(const uint32_t *Sroot, const uint32_t *V, const uint32_t *Croot, size_t stride, int logS, int log2M,
-                       int nwin, int c, uint32_t *wsum, uint32_t *out, cudaStream_t st);
+                       int nwin, int c, int split_top, uint32_t *wsum, uint32_t *out, cudaStream_t st);
 void launch_sum_partials_g1(const uint32_t *partials, int count, uint32_t *out, cudaStream_t st);
 void launch_sum_partials_g2(const uint32_t *partials, int count, uint32_t *out, cudaStream_t st);
 

@@ -102,7 +102,8 @@ k_tree_level(const uint32_t *__restrict__ Sin, size_t sin_stride, const uint32_t
 template <class F>
 __global__ void __launch_bounds__(128)
 k_combine(const uint32_t *__restrict__ Sroot, const uint32_t *__restrict__ V, const uint32_t *__restrict__ Croot,
-          size_t stride, int logS, int log2M, int nwin, int c, uint32_t *__restrict__ wsum, uint32_t *__restrict__ out) {
+          size_t stride, int logS, int log2M, int nwin, int c, int split_top, uint32_t *__restrict__ wsum,
+          uint32_t *__restrict__ out) {
     constexpr int W = field_words<F>::value;
     constexpr int PW = 4 * W;
     const int qd = threadIdx.x >> 2;
@@ -123,13 +124,26 @@ k_combine(const uint32_t *__restrict__ Sroot, const uint32_t *__restrict__ V, co
         }
         q_load(a, Sroot + (size_t)w * stride * PW);
         q_add(acc, a);
+        if (split_top) {                           // upper half of the unsigned top digit: + 2^(c−1)·Σ buckets
+            const bool extra = w == nwin - 1;      // (every quad runs the chain: q_dbl needs whole warps)
+            for (int k = 0; k < c - 1; k++) q_dbl(a);
+            F zero;
+            q_set_inf(zero);
+            a = q_sel(extra, a, zero);
+            q_add(acc, a);
+        }
         if (base + qd < nwin) q_store(wsum + (size_t)(base + qd) * PW, acc);
     }
     __syncthreads();                               // window sums visible to warp 0
     if (threadIdx.x >= 32) return;                 // warp 0 finishes (its 8 quads in lock-step)
     q_set_inf(acc);
-    for (int ww = nwin - 1; ww >= 0; ww--) {
-        if (ww != nwin - 1)                        // nothing to double before the top window
+    int top = nwin - 1;
+    if (split_top) {                               // the two halves of the top digit share one weight
+        q_load(acc, wsum + (size_t)top * PW);
+        top--;
+    }
+    for (int ww = top; ww >= 0; ww--) {
+        if (ww != top)                             // nothing to double before the top window
             for (int k = 0; k < c; k++) q_dbl(acc);
         q_load(a, wsum + (size_t)ww * PW);
         q_add(acc, a);

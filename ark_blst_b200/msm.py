@@ -200,6 +200,12 @@ def imad_peak():
     return {"imad_per_s": out[0], "imad_wide_x2_per_s": out[1], "sm_mhz_est": out[2]}
 
 
+def last_plan():
+    out = (ctypes.c_int * 4)()
+    _lib.check(lib.b200msm_last_plan(out), "last_plan")
+    return {"window_bits": out[0], "windows": out[1], "glv": out[2], "table": out[3]}
+
+
 def last_phase_ms():
     out = (ctypes.c_double * 8)()
     _lib.check(lib.b200msm_last_phase_ms(out), "last_phase_ms")

@@ -240,6 +240,7 @@ def run_ours(args):
         ev[k][1].record()
         ev[k][1].synchronize()
         phases.append(eng.last_phase_ms())
+    plan = eng.last_plan()
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
     launches = (L.b200msm_launch_count() - launches0) / args.steps
@@ -418,7 +419,10 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "u32x12 Montgomery limbs (integer)", "data": "synthetic",
             "points_per_s": n_total / (dev_ms * 1e-3),
             "config": {"workload": f"{args.group.upper()} MSM 2^{args.logn} points per GPU x {world} GPU(s) = {n_total} points",
-                       "window_bits": c, "windows": W, "scalars": "uniform mod r, Montgomery form (VariableBaseMSM::msm)",
+                       "window_bits": c, "windows": W,
+                       "engine_plan": {**plan, "note": "glv 2 = scalars split k1 + k2*lambda over (P, phi(P)), unsigned top digit; "
+                                                       "window_bits/windows above are the canonical c* of the work model (roofline numerator)"},
+                       "scalars": "uniform mod r, Montgomery form (VariableBaseMSM::msm)",
                        "bases": "random subgroup points k_i*G, affine, resident in HBM",
                        "l2": "flushed between steps (256 MiB memset, outside the per-step events)",
                        "parity": "GPU result == (sum s_i k_i)*G and == CPU oracle result" if parity else "MISMATCH"},

@@ -133,8 +133,10 @@ unsigned long long b200msm_launch_count(void);
 
 /* Tunables (SURVEY §5 "config/flags"): window width c; 0 = automatic from n. */
 int b200msm_set_window_bits(int c);
-/* G1 only: GLV split of every scalar into two 128-bit halves over (P, φ(P)) — halves the windows
- * of the on-device Horner chain. -1 = automatic (time model), 0 = never, 1 = always. */
+/* GLV split of every scalar into two 128-bit halves k = k1 + k2·λ over (P, φ(P) = (β·x, y)) — half
+ * the scalar bits, so half the windows to reduce and half the on-device Horner chain, at the same
+ * number of bucket additions. -1 = automatic (time model; the default: on for n ≤ 2^22), 0 = never,
+ * 1 = always. Results are the same group elements either way. */
 int b200msm_set_glv(int mode);
 /* Buckets holding more than max(32, factor × mean occupancy, entries/175000) entries leave the
  * one-thread-per-bucket kernel for the block-cooperative path (0 = automatic: 3, or 4 with a
@@ -148,6 +150,9 @@ int b200msm_set_max_chunk(size_t max_points_per_pass);
  * [0] digits [1] sort [2] bucket bounds+order [3] accumulate [4] reduce [5] combine [6] total
  * [7] accumulate launches. Filled only when b200msm_set_profiling(1). */
 int b200msm_set_profiling(int on);
+/* Plan of the most recent pass on this thread's device: [0] window bits c, [1] windows,
+ * [2] GLV (0 off, 1 on, 2 on with the unsigned top digit), [3] fixed-base table used. */
+int b200msm_last_plan(int out[4]);
 int b200msm_last_phase_ms(double out[8]);
 
 /* ---- synthetic data + measurement utilities (bench / tests; not on the reference's path) ---- */

@@ -184,11 +184,12 @@ def test_chunked_passes(eng, cref, g2):
         assert cref.affine_equal(g2, got, exp), chunk
 
 
-@pytest.mark.parametrize("n", [1, 9, 700, 20000])
-def test_glv_path(eng, cref, n):
-    """G1 GLV split (k = k1 + k2·λ over P and φ(P)) — off by default, forced on here — must give
-    the same group element; includes scalars around λ and identity bases"""
-    bases = cref.synth_bases(0, 71 + n, n)
+@pytest.mark.parametrize("g2,n", [(0, 1), (0, 9), (0, 700), (0, 20000), (1, 1), (1, 9), (1, 700), (1, 6000)])
+def test_glv_path(eng, cref, g2, n):
+    """GLV split (k = k1 + k2·λ over P and φ(P) = (β·x, y); β² on G2) forced on AND forced off — the
+    automatic plan picks either — must give the same group element; includes scalars around λ and
+    identity bases"""
+    bases = cref.synth_bases(g2, 71 + n, n)
     sc_int = [o.limbs_to_int(r) for r in cref.synth_scalars(72 + n, n, False).tolist()]
     lam = o.BLS_X * o.BLS_X - 1
     for k, v in enumerate([0, 1, lam - 1, lam, lam + 1, o.R_ORDER - 1, lam * lam, (1 << 128) - 1, 1 << 128]):
@@ -197,12 +198,47 @@ def test_glv_path(eng, cref, n):
     if n > 12:
         bases[11] = 0
     sc = scalars_to_limbs(sc_int, False)
-    exp = cref.msm(0, bases, sc, 0)
+    exp = cref.msm(g2, bases, sc, 0)
     L = eng._lib.lib
-    assert L.b200msm_set_glv(1) == 0
+    for mode in (1, 0):
+        assert L.b200msm_set_glv(mode) == 0
+        try:
+            got = _grp(eng, g2).msm_bigint(bases, sc)
+            got_m = _grp(eng, g2).msm(bases, scalars_to_limbs(sc_int, True))
+        finally:
+            L.b200msm_set_glv(-1)
+        assert cref.affine_equal(g2, got, exp) and cref.affine_equal(g2, got_m, exp), mode
+
+
+@pytest.mark.parametrize("g2,c", [(0, 4), (0, 8), (0, 13), (0, 16), (1, 8), (1, 13), (1, 16)])
+def test_glv_window_layouts(eng, cref, g2, c):
+    """GLV with the width forced: c | 128 takes the top c bits of each 128-bit half unsigned and
+    spreads that digit over the last two windows (no carry window), other widths keep the Booth
+    carry window; halves whose top digit sits on either side of 2^(c−1), with and without the
+    carry from below, are planted explicitly"""
+    n = 3000 if not g2 else 1200
+    lam = o.BLS_X * o.BLS_X - 1
+    bases = cref.synth_bases(g2, 171 + c, n)
+    sc_int = [o.limbs_to_int(r) for r in cref.synth_scalars(172 + c, n, False).tolist()]
+    half = 1 << (c - 1)
+    tops = [half - 1, half, half + 1, (lam >> (128 - c)) - 1, 1, 0]
+    k = 0
+    for t1 in tops:
+        for carry in (0, 1):
+            for t2 in (tops[0], tops[2]):
+                k1 = (t1 << (128 - c)) | (carry << (127 - c)) | 5
+                k2 = (t2 << (128 - c)) | ((1 - carry) << (127 - c)) | 9
+                assert k1 < lam and k2 < lam
+                sc_int[k] = (k1 + k2 * lam) % o.R_ORDER
+                k += 1
+    sc = scalars_to_limbs(sc_int, False)
+    exp = cref.msm(g2, bases, sc, 0)
+    L = eng._lib.lib
+    assert L.b200msm_set_glv(1) == 0 and L.b200msm_set_window_bits(c) == 0
     try:
-        got = eng.G1Projective.msm_bigint(bases, sc)
-        got_m = eng.G1Projective.msm(bases, scalars_to_limbs(sc_int, True))
+        got = _grp(eng, g2).msm_bigint(bases, sc)
     finally:
-        L.b200msm_set_glv(0)
-    assert cref.affine_equal(0, got, exp) and cref.affine_equal(0, got_m, exp)
+        L.b200msm_set_glv(-1)
+        L.b200msm_set_window_bits(0)
+    assert cref.affine_equal(g2, got, exp)
+

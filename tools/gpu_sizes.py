@@ -9,6 +9,9 @@ from oracle import cref
 
 L = eng._lib.lib
 L.b200msm_set_profiling(1)
+import os
+if os.environ.get("GLV"): L.b200msm_set_glv(int(os.environ["GLV"]))
+if os.environ.get("WBITS"): L.b200msm_set_window_bits(int(os.environ["WBITS"]))
 peak = eng.imad_peak()["imad_per_s"]
 sys.path.insert(0, ".")
 from bench import work_model, FPMUL_IMAD
@@ -33,10 +36,11 @@ for spec in sys.argv[1:]:
         ms = e0.elapsed_time(e1)
         if it and (best is None or ms < best): best = ms
     ph = eng.last_phase_ms()
+    plan = eng.last_plan()
     exp = cref.msm_by_dlog(g2, 1, cref.synth_scalars(2, n, False))
     ok = cref.affine_equal(g2, out.cpu().numpy().view(np.uint64), exp)
     c, W, tot, acc = work_model(n, g2)
-    print(json.dumps({"group": g, "logn": int(logn), "c": c, "W": W, "gen_s": round(tg, 2), "ms": round(best, 3), "parity": bool(ok),
+    print(json.dumps({"group": g, "logn": int(logn), "c*": c, "W*": W, "plan": plan, "gen_s": round(tg, 2), "ms": round(best, 3), "parity": bool(ok),
                       "msm_frac_of_imad_peak": round(tot * FPMUL_IMAD / (best * 1e-3) / peak, 3),
                       "acc_frac": round(acc * FPMUL_IMAD / (ph["accumulate"] * 1e-3) / peak, 3),
                       "mem_gb": round(torch.cuda.mem_get_info()[1] / 1e9 - torch.cuda.mem_get_info()[0] / 1e9, 1),
