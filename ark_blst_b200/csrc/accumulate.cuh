@@ -29,7 +29,8 @@ template <class F>
 __global__ void __launch_bounds__(128)
 k_accumulate(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ vals,
              const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, uint32_t nb,
-             uint32_t heavy_thr, const uint32_t *__restrict__ endo_x, uint32_t n_pts, uint32_t *__restrict__ buckets) {
+             uint32_t heavy_thr, const uint32_t *__restrict__ endo_x, uint32_t n_pts, int into,
+             uint32_t *__restrict__ buckets) {
     constexpr int W = field_words<F>::value;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nb) return;
@@ -37,7 +38,12 @@ k_accumulate(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ va
     uint32_t s = start[b], e = start[b + 1];
     if (e - s > heavy_thr) return;  // written by k_heavy_final
     xyzz<F> acc;
-    xyzz_set_inf(acc);
+    // `into`: a later slice of a streamed MSM (the bases arrive from the host in slices, every slice
+    // is accumulated into the same buckets, one reduction at the end) continues from the bucket
+    if (into) {
+        if (s == e) return;
+        xyzz_load(acc, buckets + (size_t)b * (4 * W));
+    } else xyzz_set_inf(acc);
     uint32_t v = s < e ? vals[s] : 0;
     for (uint32_t j = s; j < e; j++) {
         // index ≥ n_pts (GLV): the endomorphism image φ(P) = (β·x, y) of point index − n_pts, whose
@@ -197,7 +203,7 @@ k_heavy_tasks(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ v
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_heavy_final(const HeavyHeader *__restrict__ hdr, const HeavyBucket *__restrict__ hb,
-              const uint32_t *__restrict__ partials, uint32_t *__restrict__ buckets) {
+              const uint32_t *__restrict__ partials, int into, uint32_t *__restrict__ buckets) {
     constexpr int PW = 4 * field_words<F>::value;
     __shared__ __align__(16) uint32_t smem[(THREADS / 2) * PW];
     const uint32_t nh = hdr->n_heavy;
@@ -210,7 +216,13 @@ k_heavy_final(const HeavyHeader *__restrict__ hdr, const HeavyBucket *__restrict
             xyzz_add_ni(acc, o);
         }
         if (B.n_tasks > 1) block_tree_sum<F, THREADS>(acc, smem);  // block-uniform condition
-        if (threadIdx.x == 0) xyzz_store(buckets + (size_t)B.bucket * PW, acc);
+        if (threadIdx.x == 0) {
+            if (into) {                            // streamed MSM: earlier slices already fed this bucket
+                xyzz_load(o, buckets + (size_t)B.bucket * PW);
+                xyzz_add_ni(acc, o);
+            }
+            xyzz_store(buckets + (size_t)B.bucket * PW, acc);
+        }
     }
 }
 

@@ -178,6 +178,7 @@ struct DeviceCtx {
     DevBuf bases, scalars, digits, vals, start, cnt, ord, buckets, lvlR[2], lvlC[2], out;
     DevBuf hvy_hdr, hvy_buckets, hvy_tasks, hvy_partials, treeS[2], treeV[2], treeC[2], wsum, chunk_partials, norm_in, norm_out, tile_sums, size_hist, endo, tbl_tmp;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_slice[16] = {};  // per slice of a streamed MSM: scalars ready, bases ready
     double phase_ms[8] = {};
     int last_plan[4] = {0, 0, 0, 0};  // c, windows, GLV (0/1/2 = off / on / on with the unsigned top digit), table
     bool phase_pending = false;
@@ -207,6 +208,8 @@ struct Engine {
     size_t max_chunk_override = 0;
     int glv_mode = -1;  // -1 automatic (time model; default), 0 never, 1 always
     bool profiling = false;
+    int stream_slices = 8;          // (at most) host-buffer MSMs of ≥ stream_min points per device are uploaded and accumulated in slices
+    size_t stream_min = 1u << 18;
     int heavy_factor = 0;  // a bucket is heavy above heavy_factor × the mean occupancy (see run_pass); 0 = automatic
 };
 Engine g_eng;
@@ -242,6 +245,7 @@ int engine_init_locked(int first, int ndev) {
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         CUDA_TRY(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
         for (auto &ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
+        for (auto &ev : c->ev_slice) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         g_eng.ctx.push_back(std::move(c));
     }
     g_eng.inited = true;
@@ -263,20 +267,28 @@ DeviceCtx *ctx_for_current_device() {
 // Must be called with ctx.mu held and ctx.dev current. Asynchronous on `st`.
 // `bases_ready` (optional): an event after which d_bases is valid — the scalar-side phases
 // (digits, sort, bucket offsets) do not read the bases, so they overlap the bases' H2D copy.
+// Streamed MSM (host bases arriving in slices): every slice is grouped and accumulated into the
+// SAME buckets under one plan — `plan` fixed by the caller, `into` for every slice but the first —
+// and only the last one (`finish`) runs the reduction and the combination.
+struct PassOpts {
+    const Plan *plan = nullptr;
+    bool into = false, finish = true;
+};
 int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scalars_v, size_t n, int mont, void *d_out_v,
-              cudaStream_t st, cudaEvent_t bases_ready = nullptr, const TableRef *tbl = nullptr) {
+              cudaStream_t st, cudaEvent_t bases_ready = nullptr, const TableRef *tbl = nullptr, const PassOpts &po = PassOpts()) {
     if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "group must be B200MSM_G1 or B200MSM_G2");
     const bool g2 = group == B200MSM_G2;
     const uint32_t *d_bases = (const uint32_t *)d_bases_v, *d_scalars = (const uint32_t *)d_scalars_v;
     uint32_t *d_out = (uint32_t *)d_out_v;
     const int W = g2 ? 24 : 12;                      // u32 words per field element
     const size_t PB = 4 * (size_t)W * sizeof(uint32_t);  // bytes per XYZZ point
-    if (n == 0) {
+    if (n == 0 && !po.plan) {
         CUDA_TRY(cudaMemsetAsync(d_out, 0, 3 * W * 4, st));
         return 0;
     }
     Plan pl;
-    if (tbl) {  // the table fixes the width
+    if (po.plan) pl = *po.plan;
+    else if (tbl) {  // the table fixes the width
         pl.c = tbl->c;
         pl.nwin = tbl->nwin;
         pl.glv = pl.split = false;
@@ -349,13 +361,17 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     CUDA_TRY(cudaEventRecord(cx.ev_fork, st));
     CUDA_TRY(cudaStreamWaitEvent(cx.aux_stream, cx.ev_fork, 0));
     (g2 ? launch_heavy_g2 : launch_heavy_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, endo_x, n_pts, cx.hvy_hdr.p,
-                                             cx.hvy_buckets.p, cx.hvy_tasks.p, cx.hvy_partials.as<uint32_t>(),
+                                             cx.hvy_buckets.p, cx.hvy_tasks.p, cx.hvy_partials.as<uint32_t>(), po.into ? 1 : 0,
                                              cx.buckets.as<uint32_t>(), cx.sm_count * 4, cx.aux_stream);
     CUDA_TRY(cudaEventRecord(cx.ev_join, cx.aux_stream));
-    (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, endo_x, n_pts,
+    (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, endo_x, n_pts, po.into ? 1 : 0,
                                                        cx.buckets.as<uint32_t>(), st);
     CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_join, 0));
     mark();
+    if (!po.finish) {
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     // 5. per-window weighted bucket sums: running-sum levels of fan-in 32 while the arrays are long
     //    (throughput-bound), then a log-depth tree (latency-bound part)
     const uint32_t *X = cx.buckets.as<uint32_t>();
@@ -520,6 +536,47 @@ struct b200msm_bases {
 
 namespace {
 
+// One device's share of a host-buffer MSM, streamed: the points are cut into slices whose uploads
+// (scalars, then bases) queue back to back on the copy stream while the compute stream groups
+// and accumulates slice k into the shared buckets as soon as it has landed — the PCIe transfer
+// of slices 1.. hides behind the accumulation of the slices before them, and the reduction and
+// combination run once.  Result in cx.out; asynchronous.  ctx.mu held, ctx.dev current.
+int msm_streamed(int group, DeviceCtx &cx, const void *h_bases, const uint64_t *h_scalars, size_t n, int mont) {
+    const bool g2 = group == B200MSM_G2;
+    const size_t AB = aff_bytes(group);
+    // ≈2^17 points per slice (measured best: 2 slices at 2^18, 4 at 2^19, 8 from 2^20 up), unless forced (stream_min < 2^17)
+    const size_t per = std::min<size_t>((size_t)1 << 17, std::max<size_t>(g_eng.stream_min, 1));
+    const int K = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(g_eng.stream_slices, 8), n / per));
+    Plan pl;
+    auto_plan(n, g2, g_eng.glv_mode, std::min(g_eng.window_override, 22), pl);
+    if (pass_scratch_bytes(n, g2, g_eng.window_override) > (size_t)60 << 30) return fail(B200MSM_ENOMEM, "streamed MSM too large");
+    if (int rc = cx.bases.reserve(n * AB)) return rc;
+    if (cx.busy_valid) CUDA_TRY(cudaStreamWaitEvent(cx.stream, cx.ev_busy, 0));
+    // the previous call's kernels may still read cx.scalars / cx.bases: copies wait for them too
+    if (cx.busy_valid) CUDA_TRY(cudaStreamWaitEvent(cx.copy_stream, cx.ev_busy, 0));
+    for (int k = 0; k < K; k++) {
+        const size_t lo = n * k / K, hi = n * (k + 1) / K;
+        cudaMemcpyAsync((char *)cx.scalars.p + lo * 32, h_scalars + 4 * lo, (hi - lo) * 32, cudaMemcpyHostToDevice, cx.copy_stream);
+        cudaEventRecord(cx.ev_slice[2 * k], cx.copy_stream);
+        cudaMemcpyAsync((char *)cx.bases.p + lo * AB, (const char *)h_bases + lo * AB, (hi - lo) * AB, cudaMemcpyHostToDevice, cx.copy_stream);
+        cudaEventRecord(cx.ev_slice[2 * k + 1], cx.copy_stream);
+    }
+    for (int k = 0; k < K; k++) {
+        const size_t lo = n * k / K, hi = n * (k + 1) / K;
+        PassOpts po;
+        po.plan = &pl;
+        po.into = k > 0;
+        po.finish = k == K - 1;
+        CUDA_TRY(cudaStreamWaitEvent(cx.stream, cx.ev_slice[2 * k], 0));
+        if (int rc = run_pass(group, cx, (const char *)cx.bases.p + lo * AB, (const char *)cx.scalars.p + lo * 32, hi - lo, mont, cx.out.p,
+                              cx.stream, cx.ev_slice[2 * k + 1], nullptr, po))
+            return rc;
+    }
+    CUDA_TRY(cudaEventRecord(cx.ev_busy, cx.stream));
+    cx.busy_valid = true;
+    return 0;
+}
+
 int msm_host(int group, const uint64_t *bases, const uint64_t *scalars, size_t n, int mont, uint64_t *out,
              const b200msm_bases *resident) {
     if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "bad group");
@@ -557,6 +614,10 @@ int msm_host(int group, const uint64_t *bases, const uint64_t *scalars, size_t n
             continue;
         }
         if ((rc = cx.scalars.reserve(cnt[d] * 32))) break;
+        if (!resident && cnt[d] >= g_eng.stream_min && g_eng.stream_slices > 1) {
+            rc = msm_streamed(group, cx, (const char *)bases + lo[d] * AB, scalars + 4 * lo[d], cnt[d], mont);
+            continue;
+        }
         // scalars first (the digit kernel needs them), then the bases behind them on the same copy
         // stream; the compute stream only waits for the bases right before the accumulation
         cudaMemcpyAsync(cx.scalars.p, scalars + 4 * lo[d], cnt[d] * 32, cudaMemcpyHostToDevice, cx.copy_stream);
@@ -625,6 +686,7 @@ void b200msm_shutdown(void) {
         cudaStreamSynchronize(c->stream);
         c->release_all();
         for (auto &ev : c->ev) cudaEventDestroy(ev);
+        for (auto &ev : c->ev_slice) cudaEventDestroy(ev);
         cudaStreamDestroy(c->stream);
         cudaStreamDestroy(c->copy_stream);
         cudaEventDestroy(c->ev_scalars);
@@ -895,6 +957,12 @@ int b200msm_serialize(int group, const uint64_t *affine, size_t n, int compresse
 int b200msm_set_window_bits(int c) {
     if (c < 0 || c == 1 || c > 24) return fail(B200MSM_EINVAL, "window bits must be 0 (auto) or 2..24");
     g_eng.window_override = c;
+    return 0;
+}
+int b200msm_set_stream_slices(int slices, size_t min_points) {
+    if (slices < 1 || slices > 8) return fail(B200MSM_EINVAL, "stream slices must be 1 (off) .. 8");
+    g_eng.stream_slices = slices;
+    g_eng.stream_min = min_points ? min_points : (size_t)1 << 18;
     return 0;
 }
 int b200msm_set_heavy_factor(int f) {

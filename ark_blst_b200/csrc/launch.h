@@ -25,18 +25,20 @@ constexpr uint32_t HEAVY_CHUNK = 4096;  // entries per block task of a heavy buc
 // endo_x / n_pts: GLV: value indices ≥ n_pts name φ(P) = (β·x, y) of point index − n_pts, x read from
 // the β·x table; pass nullptr / 0xffffffff when unused
 void launch_accumulate_g1(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
-                          uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, uint32_t *buckets, cudaStream_t st);
+                          uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, int into, uint32_t *buckets,
+                          cudaStream_t st);
 void launch_accumulate_g2(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
-                          uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, uint32_t *buckets, cudaStream_t st);
+                          uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, int into, uint32_t *buckets,
+                          cudaStream_t st);
 void launch_endo_table_g1(const uint32_t *bases, size_t n, uint32_t *endo_x, cudaStream_t st);
 void launch_endo_table_g2(const uint32_t *bases, size_t n, uint32_t *endo_x, cudaStream_t st);
 // plan + block tasks + per-bucket fold for buckets above heavy_thr; hdr must be zeroed (8 bytes)
 void launch_heavy_g1(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
                      uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, void *hdr, void *hb, void *tasks,
-                     uint32_t *partials, uint32_t *buckets, int grid, cudaStream_t st);
+                     uint32_t *partials, int into, uint32_t *buckets, int grid, cudaStream_t st);
 void launch_heavy_g2(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
                      uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, void *hdr, void *hb, void *tasks,
-                     uint32_t *partials, uint32_t *buckets, int grid, cudaStream_t st);
+                     uint32_t *partials, int into, uint32_t *buckets, int grid, cudaStream_t st);
 // jac_out[i] = 2^c · prev[i] (affine in, Jacobian out): one window step of the table build
 void launch_table_shift_g1(const uint32_t *prev, size_t n, int c, uint32_t *jac_out, cudaStream_t st);
 void launch_table_shift_g2(const uint32_t *prev, size_t n, int c, uint32_t *jac_out, cudaStream_t st);

@@ -109,4 +109,37 @@ struct G2Projective {                    // blst_p2 (Jacobian)
 };
 static_assert(sizeof(G1Projective) == 144 && sizeof(G2Projective) == 288, "projective layout");
 
+// Resident bases: a proving key's bases uploaded once, many scalar vectors run
+// against them. The reference has no counterpart — its GPU arm re-uploads the bases and rebuilds
+// the program on every call (src/gpu.rs:149-150,233-237). `precompute()` turns the upload into a
+// fixed-base window table (b200msm_bases_precompute): one bucket set, no Horner chain.
+template <class Proj> class ResidentBases {
+    b200msm_bases *h_ = nullptr;
+    usize n_ = 0;
+    static constexpr int group() { return sizeof(Proj) == 144 ? B200MSM_G1 : B200MSM_G2; }
+
+  public:
+    using Affine = typename Proj::MulBase;
+    ResidentBases(const Affine *bases, usize n) : n_(n) {
+        if (b200msm_bases_upload(group(), reinterpret_cast<const uint64_t *>(bases), n, &h_) != 0)
+            throw std::string("bases_upload: ") + b200msm_last_error();
+    }
+    ResidentBases(const ResidentBases &) = delete;
+    ResidentBases &operator=(const ResidentBases &) = delete;
+    ~ResidentBases() { b200msm_bases_free(h_); }
+    usize len() const { return n_; }
+    bool precompute(int window_bits = 0) { return b200msm_bases_precompute(h_, window_bits) == 0; }
+    // same error convention as VariableBaseMSM::msm: more scalars than bases → Err(min(len)), device error → Err(0)
+    Result<Proj> msm(const Scalar *scalars, usize ns) const { return run(reinterpret_cast<const uint64_t *>(scalars), ns, 1); }
+    Result<Proj> msm_bigint(const BigInt4 *bigints, usize ns) const { return run(reinterpret_cast<const uint64_t *>(bigints), ns, 0); }
+
+  private:
+    Result<Proj> run(const uint64_t *scalars, usize ns, int mont) const {
+        if (ns > n_) return Result<Proj>::Err(n_);
+        Proj out{};
+        if (b200msm_run(h_, scalars, ns, mont, out.l) != 0) return Result<Proj>::Err(0);
+        return Result<Proj>::Ok(out);
+    }
+};
+
 }  // namespace ark_blst

@@ -138,6 +138,12 @@ int b200msm_set_window_bits(int c);
  * number of bucket additions. -1 = automatic (time model; the default: on for n ≤ 2^22), 0 = never,
  * 1 = always. Results are the same group elements either way. */
 int b200msm_set_glv(int mode);
+/* One-shot host-buffer MSMs (b200msm_g1 / b200msm_g2) of at least `min_points` per device
+ * (0 = default 2^18) upload their inputs in up to `slices` pieces of ≈2^17 points (default 8,
+ * 1 = off): slice k is
+ * grouped and accumulated into the shared buckets while slice k+1 crosses PCIe; reduction and
+ * combination run once. */
+int b200msm_set_stream_slices(int slices, size_t min_points);
 /* Buckets holding more than max(32, factor × mean occupancy, entries/175000) entries leave the
  * one-thread-per-bucket kernel for the block-cooperative path (0 = automatic: 3, or 4 with a
  * fixed-base table). */

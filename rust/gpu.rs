@@ -21,6 +21,11 @@ type c_int = core::ffi::c_int;
 extern "C" {
     fn b200msm_g1(bases: *const u64, scalars: *const u64, n: usize, scalars_are_montgomery: c_int, out: *mut u64) -> c_int;
     fn b200msm_g2(bases: *const u64, scalars: *const u64, n: usize, scalars_are_montgomery: c_int, out: *mut u64) -> c_int;
+    // resident bases (a proving key uploaded once) and their fixed-base window table
+    fn b200msm_bases_upload(group: c_int, bases: *const u64, n: usize, handle: *mut *mut core::ffi::c_void) -> c_int;
+    fn b200msm_bases_precompute(handle: *mut core::ffi::c_void, window_bits: c_int) -> c_int;
+    fn b200msm_run(handle: *const core::ffi::c_void, scalars: *const u64, n: usize, scalars_are_montgomery: c_int, out: *mut u64) -> c_int;
+    fn b200msm_bases_free(handle: *mut core::ffi::c_void) -> c_int;
 }
 
 // The casts below are sound only because every wrapper is #[repr(transparent)] over the blst type
@@ -88,3 +93,38 @@ pub(crate) fn msm_g2(bases: &[G2Affine], scalars: Scalars<'_>) -> Result<G2Proje
 // keep the generic bound the old entry point had so call sites outside g1.rs/g2.rs still name it
 #[allow(dead_code)]
 pub(crate) fn _assert_affine<G: AffineRepr>() {}
+
+/// A proving key's G1 bases kept on the device(s): `upload` once, `msm` per proof (32 B/point of
+/// H2D instead of 128). `precompute` turns them into a fixed-base window table (no Horner chain,
+/// one-window bucket reduction). The reference has no counterpart: it re-uploads the bases and
+/// rebuilds its program on every call (src/gpu.rs:149-150,233-237).
+pub struct ResidentG1Bases {
+    handle: *mut core::ffi::c_void,
+    len: usize,
+}
+unsafe impl Send for ResidentG1Bases {}
+unsafe impl Sync for ResidentG1Bases {}
+
+impl ResidentG1Bases {
+    pub fn upload(bases: &[G1Affine]) -> Result<Self, usize> {
+        let mut handle = core::ptr::null_mut();
+        let rc = unsafe { b200msm_bases_upload(0, bases.as_ptr() as *const u64, bases.len(), &mut handle) };
+        if rc != 0 { Err(0) } else { Ok(Self { handle, len: bases.len() }) }
+    }
+    pub fn precompute(&mut self) -> Result<(), usize> {
+        if unsafe { b200msm_bases_precompute(self.handle, 0) } != 0 { Err(0) } else { Ok(()) }
+    }
+    pub fn msm(&self, scalars: &[Scalar]) -> Result<G1Projective, usize> {
+        if scalars.len() > self.len {
+            return Err(self.len);
+        }
+        let mut out = core::mem::MaybeUninit::<G1Projective>::uninit();
+        let rc = unsafe { b200msm_run(self.handle, scalars.as_ptr() as *const u64, scalars.len(), 1, out.as_mut_ptr() as *mut u64) };
+        if rc != 0 { Err(0) } else { Ok(unsafe { out.assume_init() }) }
+    }
+}
+impl Drop for ResidentG1Bases {
+    fn drop(&mut self) {
+        unsafe { b200msm_bases_free(self.handle) };
+    }
+}

@@ -75,6 +75,26 @@ int main(int argc, char **argv) {
         CHECK(res.is_ok());
         CHECK((same_point<G2Projective, 24>(res.unwrap(), exp, ref_g2_to_affine)));
     }
+    {   // resident bases, plain and as a fixed-base window table: same group element as msm()
+        const size_t n = 300;
+        std::vector<G1Affine> bases(n);
+        std::vector<Scalar> scalars(n);
+        ref_synth_bases(0, 6262, n, g1, bases[0].l, 1);
+        ref_synth_scalars(6363, n, 1, scalars[0].l);
+        auto direct = G1Projective::msm(bases.data(), n, scalars.data(), n);
+        CHECK(direct.is_ok());
+        ResidentBases<G1Projective> pk(bases.data(), n);
+        auto r1 = pk.msm(scalars.data(), n);
+        CHECK(r1.is_ok() && (same_point<G1Projective, 12>(r1.unwrap(), direct.unwrap().l, ref_g1_to_affine)));
+        CHECK(pk.precompute());
+        auto r2 = pk.msm(scalars.data(), n);
+        CHECK(r2.is_ok() && (same_point<G1Projective, 12>(r2.unwrap(), direct.unwrap().l, ref_g1_to_affine)));
+        auto r3 = pk.msm(scalars.data(), 100);   // prefix
+        auto d3 = G1Projective::msm(bases.data(), 100, scalars.data(), 100);
+        CHECK(r3.is_ok() && (same_point<G1Projective, 12>(r3.unwrap(), d3.unwrap().l, ref_g1_to_affine)));
+        std::vector<Scalar> more(n + 1);
+        CHECK(pk.msm(more.data(), n + 1).is_err() && pk.msm(more.data(), n + 1).unwrap_err() == n);
+    }
     std::printf(failures ? "FAILED (%d)\n" : "ok\n", failures);
     return failures ? 1 : 0;
 }

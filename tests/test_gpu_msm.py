@@ -242,3 +242,29 @@ def test_glv_window_layouts(eng, cref, g2, c):
         L.b200msm_set_window_bits(0)
     assert cref.affine_equal(g2, got, exp)
 
+
+@pytest.mark.parametrize("g2,n,slices", [(0, 5, 8), (0, 1000, 2), (0, 20001, 4), (0, 20001, 8), (1, 3000, 4)])
+def test_streamed_host_msm(eng, cref, g2, n, slices):
+    """one-shot host-buffer MSM with the upload cut into slices that are accumulated into shared
+    buckets (forced at small n here; the default starts at 2^18 points): same group element, with
+    GLV on and off, uniform and witness-like scalars (heavy buckets fed by several slices)"""
+    L = eng._lib.lib
+    bases = cref.synth_bases(g2, 900 + n, n)
+    rng = random.Random(n)
+    uni = [o.limbs_to_int(r) for r in cref.synth_scalars(901 + n, n, False).tolist()]
+    wit = [0 if (u := rng.random()) < 0.3 else 1 if u < 0.7 else rng.randrange(1 << 32) if u < 0.8 else uni[i] for i in range(n)]
+    assert L.b200msm_set_stream_slices(slices, 1) == 0
+    try:
+        for sc_int in (uni, wit):
+            sc = scalars_to_limbs(sc_int, False)
+            exp = cref.msm(g2, bases, sc, 0)
+            for mode in (-1, 0, 1):
+                assert L.b200msm_set_glv(mode) == 0
+                got = _grp(eng, g2).msm_bigint(bases, sc)
+                assert cref.affine_equal(g2, got, exp), (mode, sc_int is wit)
+            got = _grp(eng, g2).msm(bases, scalars_to_limbs(sc_int, True))
+            assert cref.affine_equal(g2, got, exp)
+    finally:
+        L.b200msm_set_glv(-1)
+        L.b200msm_set_stream_slices(8, 0)
+
