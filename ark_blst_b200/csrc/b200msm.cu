@@ -167,7 +167,9 @@ int table_plan(size_t n, bool g2) {
 }
 
 struct DeviceCtx {
-    int dev = -1;
+    int dev = -1, lane = 0;
+    cudaStream_t tail_stream = nullptr;            // high priority: the latency-bound reduction + combination
+    cudaEvent_t ev_tail_fork = nullptr, ev_tail_join = nullptr;
     std::mutex mu;
     cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
     cudaEvent_t ev_scalars = nullptr, ev_bases = nullptr, ev_busy = nullptr, ev_fork = nullptr, ev_join = nullptr;
@@ -204,6 +206,9 @@ struct Engine {
     std::mutex mu;
     bool inited = false;
     std::vector<std::unique_ptr<DeviceCtx>> ctx;
+    // extra lanes (b200msm_set_lane): further contexts on the same devices with their own scratch, so that MSMs
+    // issued on different streams overlap — one's latency-bound tail under another's accumulation
+    std::vector<std::unique_ptr<DeviceCtx>> lane_ctx;
     int window_override = 0;
     size_t max_chunk_override = 0;
     int glv_mode = -1;  // -1 automatic (time model; default), 0 never, 1 always
@@ -213,6 +218,45 @@ struct Engine {
     int heavy_factor = 0;  // a bucket is heavy above heavy_factor × the mean occupancy (see run_pass); 0 = automatic
 };
 Engine g_eng;
+
+int make_ctx(int d, int lane, int sm_count, std::unique_ptr<DeviceCtx> &out) {
+    auto c = std::make_unique<DeviceCtx>();
+    c->dev = d;
+    c->lane = lane;
+    c->sm_count = sm_count;
+    CUDA_TRY(cudaSetDevice(d));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_scalars, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_bases, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_busy, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    int lo_pri = 0, hi_pri = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    CUDA_TRY(cudaStreamCreateWithPriority(&c->tail_stream, cudaStreamNonBlocking, hi_pri));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_tail_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_tail_join, cudaEventDisableTiming));
+    for (auto &ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
+    for (auto &ev : c->ev_slice) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    out = std::move(c);
+    return 0;
+}
+void destroy_ctx(DeviceCtx &c) {
+    std::lock_guard<std::mutex> l2(c.mu);
+    cudaSetDevice(c.dev);
+    cudaStreamSynchronize(c.stream);
+    cudaStreamSynchronize(c.tail_stream);
+    c.release_all();
+    for (auto &ev : c.ev) cudaEventDestroy(ev);
+    for (auto &ev : c.ev_slice) cudaEventDestroy(ev);
+    cudaStreamDestroy(c.stream);
+    cudaStreamDestroy(c.copy_stream);
+    cudaStreamDestroy(c.aux_stream);
+    cudaStreamDestroy(c.tail_stream);
+    for (cudaEvent_t e : {c.ev_scalars, c.ev_bases, c.ev_busy, c.ev_fork, c.ev_join, c.ev_tail_fork, c.ev_tail_join}) cudaEventDestroy(e);
+}
 
 int engine_init_locked(int first, int ndev) {
     if (g_eng.inited) return 0;
@@ -232,20 +276,8 @@ int engine_init_locked(int first, int ndev) {
         if (p.major != 10)
             return fail(B200MSM_ENODEV, std::string("device ") + std::to_string(d) + " (" + p.name + ") is sm_" +
                                             std::to_string(p.major * 10 + p.minor) + "; this build is sm_100a only");
-        auto c = std::make_unique<DeviceCtx>();
-        c->dev = d;
-        c->sm_count = p.multiProcessorCount;
-        CUDA_TRY(cudaSetDevice(d));
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_scalars, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_bases, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_busy, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
-        for (auto &ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
-        for (auto &ev : c->ev_slice) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        std::unique_ptr<DeviceCtx> c;
+        if (int rc = make_ctx(d, 0, p.multiProcessorCount, c)) return rc;
         g_eng.ctx.push_back(std::move(c));
     }
     g_eng.inited = true;
@@ -255,12 +287,21 @@ int engine_init(int first, int ndev) {
     std::lock_guard<std::mutex> lk(g_eng.mu);
     return engine_init_locked(first, ndev);
 }
+thread_local int t_lane = 0;
 DeviceCtx *ctx_for_current_device() {
     int d = 0;
     cudaGetDevice(&d);
+    DeviceCtx *base = nullptr;
     for (auto &c : g_eng.ctx)
-        if (c->dev == d) return c.get();
-    return nullptr;
+        if (c->dev == d) base = c.get();
+    if (!base || t_lane == 0) return base;
+    std::lock_guard<std::mutex> lk(g_eng.mu);
+    for (auto &c : g_eng.lane_ctx)
+        if (c->dev == d && c->lane == t_lane) return c.get();
+    std::unique_ptr<DeviceCtx> c;
+    if (make_ctx(d, t_lane, base->sm_count, c)) return nullptr;
+    g_eng.lane_ctx.push_back(std::move(c));
+    return g_eng.lane_ctx.back().get();
 }
 
 // The pipeline on one device. Inputs already in device memory; d_out receives 3 field elements.
@@ -373,7 +414,15 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
         return 0;
     }
     // 5. per-window weighted bucket sums: running-sum levels of fan-in 32 while the arrays are long
-    //    (throughput-bound), then a log-depth tree (latency-bound part)
+    //    (throughput-bound), then a log-depth tree (latency-bound part).  From here on the pass is a
+    //    chain of small dependent launches: it moves to the context's high-priority stream, so that
+    //    when another lane's accumulation fills the GPU these blocks take the next free slots.
+    const cudaStream_t caller_st = st;
+    if (!prof) {
+        CUDA_TRY(cudaEventRecord(cx.ev_tail_fork, st));
+        CUDA_TRY(cudaStreamWaitEvent(cx.tail_stream, cx.ev_tail_fork, 0));
+        st = cx.tail_stream;
+    }
     const uint32_t *X = cx.buckets.as<uint32_t>();
     const uint32_t *Cin = nullptr;
     uint32_t len = pl.nbw;
@@ -415,6 +464,10 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     (g2 ? launch_combine_g2 : launch_combine_g1)(Sin, cx.treeV[cur].as<uint32_t>(), Cin ? Ccur : nullptr, tstride, logS, log2M,
                                                  rwin, pl.c, pl.split ? 1 : 0, cx.wsum.as<uint32_t>(), d_out, st);
     mark();
+    if (st != caller_st) {
+        CUDA_TRY(cudaEventRecord(cx.ev_tail_join, st));
+        CUDA_TRY(cudaStreamWaitEvent(caller_st, cx.ev_tail_join, 0));
+    }
     CUDA_TRY(cudaGetLastError());
     cx.phase_pending = prof;  // elapsed times are read lazily by b200msm_last_phase_ms (no sync here)
     return 0;
@@ -680,22 +733,9 @@ void b200msm_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_eng.mu);
     int prev = 0;
     cudaGetDevice(&prev);
-    for (auto &c : g_eng.ctx) {
-        std::lock_guard<std::mutex> l2(c->mu);
-        cudaSetDevice(c->dev);
-        cudaStreamSynchronize(c->stream);
-        c->release_all();
-        for (auto &ev : c->ev) cudaEventDestroy(ev);
-        for (auto &ev : c->ev_slice) cudaEventDestroy(ev);
-        cudaStreamDestroy(c->stream);
-        cudaStreamDestroy(c->copy_stream);
-        cudaEventDestroy(c->ev_scalars);
-        cudaEventDestroy(c->ev_bases);
-        cudaEventDestroy(c->ev_busy);
-        cudaEventDestroy(c->ev_fork);
-        cudaEventDestroy(c->ev_join);
-        cudaStreamDestroy(c->aux_stream);
-    }
+    for (auto &c : g_eng.ctx) destroy_ctx(*c);
+    for (auto &c : g_eng.lane_ctx) destroy_ctx(*c);
+    g_eng.lane_ctx.clear();
     g_eng.ctx.clear();
     g_eng.inited = false;
     cudaSetDevice(prev);
@@ -963,6 +1003,11 @@ int b200msm_set_stream_slices(int slices, size_t min_points) {
     if (slices < 1 || slices > 8) return fail(B200MSM_EINVAL, "stream slices must be 1 (off) .. 8");
     g_eng.stream_slices = slices;
     g_eng.stream_min = min_points ? min_points : (size_t)1 << 18;
+    return 0;
+}
+int b200msm_set_lane(int lane) {
+    if (lane < 0 || lane > 7) return fail(B200MSM_EINVAL, "lane must be 0..7");
+    t_lane = lane;
     return 0;
 }
 int b200msm_set_heavy_factor(int f) {

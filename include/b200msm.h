@@ -138,6 +138,12 @@ int b200msm_set_window_bits(int c);
  * number of bucket additions. -1 = automatic (time model; the default: on for n ≤ 2^22), 0 = never,
  * 1 = always. Results are the same group elements either way. */
 int b200msm_set_glv(int mode);
+/* Lanes: the device-pointer entry points called by THIS host thread use context `lane` (0..7,
+ * default 0) of the current device — its own scratch arena, created on first use.  MSMs issued
+ * on different lanes and different streams overlap: the latency-bound reduction/combination of
+ * one (which runs on a high-priority stream) hides under the accumulation of the next — the
+ * batched shape of a Groth16 prover (3×G1 + 1×G2 back to back).  Host-buffer calls use lane 0. */
+int b200msm_set_lane(int lane);
 /* One-shot host-buffer MSMs (b200msm_g1 / b200msm_g2) of at least `min_points` per device
  * (0 = default 2^18) upload their inputs in up to `slices` pieces of ≈2^17 points (default 8,
  * 1 = off): slice k is

@@ -76,3 +76,37 @@ def test_shard_sum_invariance_and_linearity(eng, cref):
     t_h = cref.synth_scalars(9003, n, False)
     exp = cref.add(0, cref.msm_by_dlog(0, 9001, s_h), cref.msm_by_dlog(0, 9001, t_h))
     assert cref.affine_equal(0, cref.add(0, whole, rt), exp)
+
+
+def test_lanes_overlap_on_streams(eng, cref):
+    """b200msm_set_lane: MSMs issued on different lanes and streams (a Groth16-shaped batch: G2 + 3×G1)
+    run concurrently on separate scratch arenas; every result equals the dlog closed form and the
+    lane-0, one-stream result"""
+    import torch
+
+    L = eng._lib.lib
+    n = 1 << 16
+    jobs = []
+    for k, g2 in enumerate((1, 0, 0, 0)):
+        bases, scalars = _dev_inputs(eng, torch, g2, 7000 + k, 7100 + k, n, True)
+        jobs.append((g2, bases, scalars, 7000 + k, 7100 + k))
+    serial = [_run(eng, torch, g2, b, s, n, True) for g2, b, s, _, _ in jobs]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    cur = torch.cuda.current_stream()
+    for rep in range(3):
+        outs = [torch.zeros(36 if g2 else 18, dtype=torch.int64, device="cuda") for g2, *_ in jobs]
+        try:
+            for k, (g2, b, s, _, _) in enumerate(jobs):
+                assert L.b200msm_set_lane(k % 2) == 0
+                streams[k % 2].wait_stream(cur)
+                eng.run_device(g2, b.data_ptr(), s.data_ptr(), n, True, outs[k].data_ptr(), streams[k % 2].cuda_stream)
+        finally:
+            L.b200msm_set_lane(0)
+        for st in streams:
+            cur.wait_stream(st)
+        torch.cuda.synchronize()
+        for k, (g2, b, s, sb, ss) in enumerate(jobs):
+            got = outs[k].cpu().numpy().view(np.uint64)
+            assert cref.affine_equal(g2, got, serial[k]), (rep, k)
+            assert cref.affine_equal(g2, got, cref.msm_by_dlog(g2, sb, cref.synth_scalars(ss, n, False))), (rep, k)
+
