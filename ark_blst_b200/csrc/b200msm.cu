@@ -328,6 +328,7 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
         return 0;
     }
     Plan pl;
+    if (tbl) d_bases = (const uint32_t *)tbl->p;
     if (po.plan) pl = *po.plan;
     else if (tbl) {  // the table fixes the width
         pl.c = tbl->c;
@@ -594,16 +595,21 @@ namespace {
 // and accumulates slice k into the shared buckets as soon as it has landed — the PCIe transfer
 // of slices 1.. hides behind the accumulation of the slices before them, and the reduction and
 // combination run once.  Result in cx.out; asynchronous.  ctx.mu held, ctx.dev current.
-int msm_streamed(int group, DeviceCtx &cx, const void *h_bases, const uint64_t *h_scalars, size_t n, int mont) {
+int msm_streamed(int group, DeviceCtx &cx, const void *h_bases, const void *d_resident, const TableRef *tbl,
+                 const uint64_t *h_scalars, size_t n, int mont) {
     const bool g2 = group == B200MSM_G2;
     const size_t AB = aff_bytes(group);
     // ≈2^17 points per slice (measured best: 2 slices at 2^18, 4 at 2^19, 8 from 2^20 up), unless forced (stream_min < 2^17)
     const size_t per = std::min<size_t>((size_t)1 << 17, std::max<size_t>(g_eng.stream_min, 1));
     const int K = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(g_eng.stream_slices, 8), n / per));
     Plan pl;
-    auto_plan(n, g2, g_eng.glv_mode, std::min(g_eng.window_override, 22), pl);
-    if (pass_scratch_bytes(n, g2, g_eng.window_override) > (size_t)60 << 30) return fail(B200MSM_ENOMEM, "streamed MSM too large");
-    if (int rc = cx.bases.reserve(n * AB)) return rc;
+    if (tbl) {  // resident fixed-base table: the table fixes the width, one bucket set
+        pl.c = tbl->c;
+        pl.nwin = tbl->nwin;
+        pl.nbw = pl.nb = 1u << (pl.c - 1);
+    } else auto_plan(n, g2, g_eng.glv_mode, std::min(g_eng.window_override, 22), pl);
+    if (h_bases)
+        if (int rc = cx.bases.reserve(n * AB)) return rc;
     if (cx.busy_valid) CUDA_TRY(cudaStreamWaitEvent(cx.stream, cx.ev_busy, 0));
     // the previous call's kernels may still read cx.scalars / cx.bases: copies wait for them too
     if (cx.busy_valid) CUDA_TRY(cudaStreamWaitEvent(cx.copy_stream, cx.ev_busy, 0));
@@ -611,18 +617,23 @@ int msm_streamed(int group, DeviceCtx &cx, const void *h_bases, const uint64_t *
         const size_t lo = n * k / K, hi = n * (k + 1) / K;
         cudaMemcpyAsync((char *)cx.scalars.p + lo * 32, h_scalars + 4 * lo, (hi - lo) * 32, cudaMemcpyHostToDevice, cx.copy_stream);
         cudaEventRecord(cx.ev_slice[2 * k], cx.copy_stream);
-        cudaMemcpyAsync((char *)cx.bases.p + lo * AB, (const char *)h_bases + lo * AB, (hi - lo) * AB, cudaMemcpyHostToDevice, cx.copy_stream);
-        cudaEventRecord(cx.ev_slice[2 * k + 1], cx.copy_stream);
+        if (h_bases) {
+            cudaMemcpyAsync((char *)cx.bases.p + lo * AB, (const char *)h_bases + lo * AB, (hi - lo) * AB, cudaMemcpyHostToDevice, cx.copy_stream);
+            cudaEventRecord(cx.ev_slice[2 * k + 1], cx.copy_stream);
+        }
     }
+    const char *dev_bases = h_bases ? (const char *)cx.bases.p : (const char *)d_resident;
     for (int k = 0; k < K; k++) {
         const size_t lo = n * k / K, hi = n * (k + 1) / K;
         PassOpts po;
         po.plan = &pl;
         po.into = k > 0;
         po.finish = k == K - 1;
+        TableRef sub;
+        if (tbl) { sub = *tbl; sub.p = (const char *)tbl->p + lo * AB; }  // same stride, shifted origin
         CUDA_TRY(cudaStreamWaitEvent(cx.stream, cx.ev_slice[2 * k], 0));
-        if (int rc = run_pass(group, cx, (const char *)cx.bases.p + lo * AB, (const char *)cx.scalars.p + lo * 32, hi - lo, mont, cx.out.p,
-                              cx.stream, cx.ev_slice[2 * k + 1], nullptr, po))
+        if (int rc = run_pass(group, cx, dev_bases ? dev_bases + lo * AB : nullptr, (const char *)cx.scalars.p + lo * 32, hi - lo, mont, cx.out.p,
+                              cx.stream, h_bases ? cx.ev_slice[2 * k + 1] : nullptr, tbl ? &sub : nullptr, po))
             return rc;
     }
     CUDA_TRY(cudaEventRecord(cx.ev_busy, cx.stream));
@@ -667,8 +678,13 @@ int msm_host(int group, const uint64_t *bases, const uint64_t *scalars, size_t n
             continue;
         }
         if ((rc = cx.scalars.reserve(cnt[d] * 32))) break;
-        if (!resident && cnt[d] >= g_eng.stream_min && g_eng.stream_slices > 1) {
-            rc = msm_streamed(group, cx, (const char *)bases + lo[d] * AB, scalars + 4 * lo[d], cnt[d], mont);
+        // large enough to be worth slicing (and, for resident bases, small enough for one pass per slice set)
+        if (cnt[d] >= g_eng.stream_min && g_eng.stream_slices > 1 && cnt[d] <= ((size_t)1 << 24) && !g_eng.max_chunk_override) {
+            if (!resident) rc = msm_streamed(group, cx, (const char *)bases + lo[d] * AB, nullptr, nullptr, scalars + 4 * lo[d], cnt[d], mont);
+            else if (resident->tbl_c) {
+                TableRef tr{resident->table[d].p, resident->cnt[d], resident->tbl_c, resident->tbl_nwin};
+                rc = msm_streamed(group, cx, nullptr, nullptr, &tr, scalars + 4 * lo[d], cnt[d], mont);
+            } else rc = msm_streamed(group, cx, nullptr, resident->shard[d].p, nullptr, scalars + 4 * lo[d], cnt[d], mont);
             continue;
         }
         // scalars first (the digit kernel needs them), then the bases behind them on the same copy

@@ -264,6 +264,18 @@ def test_streamed_host_msm(eng, cref, g2, n, slices):
                 assert cref.affine_equal(g2, got, exp), (mode, sc_int is wit)
             got = _grp(eng, g2).msm(bases, scalars_to_limbs(sc_int, True))
             assert cref.affine_equal(g2, got, exp)
+            # resident bases (scalars streamed against the uploaded shard), then the same handle as a table
+            L.b200msm_set_glv(-1)
+            rb = eng.ResidentBases(_grp(eng, g2), bases)
+            try:
+                assert cref.affine_equal(g2, rb.msm(sc, montgomery=False), exp)
+                rb.precompute(13 if n > 100 else 0)
+                assert cref.affine_equal(g2, rb.msm(sc, montgomery=False), exp)
+                if n > 10:
+                    h = n // 3
+                    assert cref.affine_equal(g2, rb.msm(sc[:h], montgomery=False), cref.msm(g2, bases[:h], sc[:h], 0))
+            finally:
+                rb.close()
     finally:
         L.b200msm_set_glv(-1)
         L.b200msm_set_stream_slices(8, 0)
