@@ -429,13 +429,15 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     uint32_t len = pl.nbw;
     int log2M = 0, pp = 0;
     // (a single window — table mode — goes to the tree as soon as a level would leave fewer than 4096 chains)
-    while (len > 2048 && (!tbl || len / 32 >= 4096)) {
-        (g2 ? launch_wsum_level_g2 : launch_wsum_level_g1)(X, Cin, len, 32, log2M, (uint32_t)rwin,
+    constexpr int fan_log = 5;                // fan-in 32: 16 and 8 measured equal or slower (profiles/r01_experiments.md)
+    const uint32_t fan = 1u << fan_log;
+    while (len > 2048 && (!tbl || len / fan >= 4096)) {
+        (g2 ? launch_wsum_level_g2 : launch_wsum_level_g1)(X, Cin, len, fan, log2M, (uint32_t)rwin,
                                                            cx.lvlR[pp].as<uint32_t>(), cx.lvlC[pp].as<uint32_t>(), st);
         X = cx.lvlR[pp].as<uint32_t>();
         Cin = cx.lvlC[pp].as<uint32_t>();
-        log2M += 5;
-        len /= 32;
+        log2M += fan_log;
+        len /= fan;
         pp ^= 1;
     }
     const uint32_t S = len;

@@ -128,7 +128,7 @@ int b200msm_deserialize(int group, const uint8_t *in, size_t n, int compressed, 
                         uint64_t *affine_out, uint8_t *status_out);
 int b200msm_serialize(int group, const uint64_t *affine, size_t n, int compressed, uint8_t *out);
 
-/* Cumulative count of this library's own kernel launches (CUB sort kernels excluded). */
+/* Cumulative count of this library's own kernel launches (no library kernel runs on the MSM path). */
 unsigned long long b200msm_launch_count(void);
 
 /* Tunables (SURVEY §5 "config/flags"): window width c; 0 = automatic from n. */
