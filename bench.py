@@ -498,6 +498,17 @@ def run_groth16(args):
         s = torch.empty((n, 4), dtype=torch.int64, device=dev)
         eng.synth_bases_device(g2, sb, n, b.data_ptr(), stream)
         eng.synth_scalars_device(ss, n, True, s.data_ptr(), stream)
+        canon = None
+        if args.scalars == "witness":   # ≈40 % zeros, ≈20 % ones, ≈10 % below 2^32, rest uniform (canonical form)
+            rng = np.random.default_rng(ss & 0xffffffff)
+            u = rng.random(n)
+            canon = cref.synth_scalars(ss, n, False)
+            small = rng.integers(0, 1 << 32, size=n, dtype=np.uint64)
+            canon[u < 0.7] = 0
+            canon[(u >= 0.4) & (u < 0.6), 0] = 1
+            mid = (u >= 0.6) & (u < 0.7)
+            canon[mid, 0] = small[mid]
+            s.copy_(torch.from_numpy(canon.view(np.int64)))
         tc = 0
         if args.table:  # resident proving key: fixed-base window table per MSM, built once outside the timed region
             tc, tw = eng.table_plan(g2, n)
@@ -505,7 +516,7 @@ def run_groth16(args):
             t[0].copy_(b)
             eng.table_build_device(g2, t.data_ptr(), n, tc, t.data_ptr(), stream)
             b = t
-        jobs.append((g2, b, s, sb, ss, torch.zeros(36 if g2 else 18, dtype=torch.int64, device=dev), tc))
+        jobs.append((g2, b, s, sb, ss, torch.zeros(36 if g2 else 18, dtype=torch.int64, device=dev), tc, canon))
     torch.cuda.synchronize()
     peak = eng.imad_peak()["imad_per_s"] if rank == 0 else None
 
@@ -516,22 +527,22 @@ def run_groth16(args):
         # the four MSMs go out on `lanes` engine lanes / streams (b200msm_set_lane): the latency-bound tail of one
         # overlaps the accumulation of the next; the partials are gathered once all four are in
         cur = torch.cuda.current_stream()
-        for k, (g2, b, s, _, _, part, tc) in enumerate(jobs):
+        for k, (g2, b, s, _, _, part, tc, _c) in enumerate(jobs):
             st = stream
             if lanes > 1:
                 L.b200msm_set_lane(k % lanes)
                 lane_streams[k % lanes].wait_stream(cur)
                 st = lane_streams[k % lanes].cuda_stream
             if tc:
-                eng.run_table_device(g2, b.data_ptr(), n, tc, s.data_ptr(), n, True, part.data_ptr(), st)
+                eng.run_table_device(g2, b.data_ptr(), n, tc, s.data_ptr(), n, _c is None, part.data_ptr(), st)
             else:
-                eng.run_device(g2, b.data_ptr(), s.data_ptr(), n, True, part.data_ptr(), st)
+                eng.run_device(g2, b.data_ptr(), s.data_ptr(), n, _c is None, part.data_ptr(), st)
         if lanes > 1:
             L.b200msm_set_lane(0)
             for ls in lane_streams:
                 cur.wait_stream(ls)
         outs = []
-        for g2, b, s, _, _, part, tc in jobs:
+        for g2, b, s, _, _, part, tc, _c in jobs:
             if world > 1:
                 gathered = torch.empty((world, part.numel()), dtype=torch.int64, device=dev)
                 dist.all_gather_into_tensor(gathered.view(-1), part)
@@ -560,8 +571,8 @@ def run_groth16(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     ok = True
-    for g2, b, s, sb, ss, part, _ in jobs:   # every rank checks its own partial against the dlog closed form
-        exp = cref.msm_by_dlog(g2, sb, cref.synth_scalars(ss, n, False))
+    for g2, b, s, sb, ss, part, _, canon in jobs:   # every rank checks its own partial against the dlog closed form
+        exp = cref.msm_by_dlog(g2, sb, canon if canon is not None else cref.synth_scalars(ss, n, False))
         ok = ok and cref.affine_equal(g2, part.cpu().numpy().view(np.uint64), exp)
     okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
     if world > 1:
@@ -572,7 +583,7 @@ def run_groth16(args):
             "metric": "Groth16-shaped batch: 3xG1 + 1xG2 MSM, ms per batch", "value": ms, "unit": "ms", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32x12 Montgomery limbs (integer)", "data": "synthetic",
-            "config": {"workload": f"3xG1 + 1xG2 MSM at 2^{args.logn} points each, sharded over {world} GPU(s), uniform scalars",
+            "config": {"workload": f"3xG1 + 1xG2 MSM at 2^{args.logn} points each, sharded over {world} GPU(s), {'witness-like' if args.scalars == 'witness' else 'uniform'} scalars",
                        "lanes": lanes,
                        "bases": "resident fixed-base window tables (b200msm_table_build_device, built once)" if args.table else "resident affine bases"},
             "parity_ok": bool(okt.item()),
@@ -602,6 +613,7 @@ def main():
     ap.add_argument("--workload", default="msm", choices=["msm", "groth16"])
     ap.add_argument("--ref-sample-logn", type=int, default=20, help="reference arm: points actually timed per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scalars", default="uniform", choices=["uniform", "witness"], help="groth16 workload: scalar distribution")
     ap.add_argument("--lanes", type=int, default=4, help="groth16 workload: engine lanes / streams the four MSMs are spread over (1 = back to back on one stream)")
     ap.add_argument("--table", action="store_true", help="groth16 workload: run every MSM against a resident fixed-base window table")
     ap.add_argument("--no-table", action="store_true", help="skip the resident-bases fixed-base-table leg")
