@@ -50,6 +50,7 @@ SIGNATURES = {
     "b200msm_set_profiling": (ctypes.c_int, [ctypes.c_int]),
     "b200msm_last_phase_ms": (ctypes.c_int, [f64p]),
     "b200msm_last_plan": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "b200msm_plan_query": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "b200msm_synth_bases_device": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint64, ctypes.c_size_t, vp, vp]),
     "b200msm_synth_scalars_device": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_size_t, ctypes.c_int, vp, vp]),
     "b200msm_imad_peak": (ctypes.c_int, [f64p]),

@@ -1046,6 +1046,17 @@ int b200msm_set_profiling(int on) {
     g_eng.profiling = on != 0;
     return 0;
 }
+int b200msm_plan_query(int group, size_t n, int glv_mode, int out[4]) {
+    if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "bad group");
+    if (!out || n == 0 || glv_mode < -1 || glv_mode > 1) return fail(B200MSM_EINVAL, "bad argument");
+    Plan pl;
+    auto_plan(n, group == B200MSM_G2, glv_mode, 0, pl);   // host arithmetic only: no device needed
+    out[0] = pl.c;
+    out[1] = pl.nwin;
+    out[2] = pl.glv ? (pl.split ? 2 : 1) : 0;
+    out[3] = (int)std::min<uint64_t>(pl.nb, 0x7fffffff);
+    return 0;
+}
 int b200msm_last_plan(int out[4]) {
     if (!g_eng.inited) return fail(B200MSM_EINVAL, "engine not initialised");
     DeviceCtx *cx = ctx_for_current_device();

@@ -165,6 +165,9 @@ int b200msm_set_profiling(int on);
 /* Plan of the most recent pass on this thread's device: [0] window bits c, [1] windows,
  * [2] GLV (0 off, 1 on, 2 on with the unsigned top digit), [3] fixed-base table used. */
 int b200msm_last_plan(int out[4]);
+/* The plan `auto_plan` would pick for an n-point MSM under the given GLV mode (-1 / 0 / 1), without
+ * touching a device: [0] window bits, [1] windows, [2] GLV (0 / 1 / 2), [3] buckets in all. */
+int b200msm_plan_query(int group, size_t n, int glv_mode, int out[4]);
 int b200msm_last_phase_ms(double out[8]);
 
 /* ---- synthetic data + measurement utilities (bench / tests; not on the reference's path) ---- */

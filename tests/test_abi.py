@@ -92,3 +92,51 @@ def test_cpp_mirror_compiles():
     """the C++ host mirror of VariableBaseMSM is header-only and must compile stand-alone"""
     src = '#include "ark_blst_b200/host/ark_blst_msm.hpp"\nint main(){ return ark_blst::G1Projective::NEGATION_IS_CHEAP ? 0 : 1; }\n'
     subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", ROOT, "-x", "c++", "-"], input=src, text=True, check=True)
+
+
+def _plan(eng, group, n, glv):
+    out = (ctypes.c_int * 4)()
+    assert eng._lib.lib.b200msm_plan_query(group, n, glv, out) == 0
+    return tuple(out)
+
+
+def test_planner_host_logic(eng):
+    """auto_plan needs no device. Without GLV it lands on the work model's canonical c* of SURVEY
+    §8(d) at 2^16 / 2^20 / 2^24 (13 / 16 / 20; 16 instead of 18 at 2^22, whose top window would be
+    degenerate) with c·W ≥ 256; GLV takes c = 16 with the unsigned top digit (8 + 1 windows) where
+    it was measured to pay and is never picked automatically above 2^22 points."""
+    from bench import work_model
+
+    for g in (0, 1):
+        for logn, c_exp in ((16, 13), (20, 16), (22, 16), (24, 20)):
+            c, W, glv, nb = _plan(eng, g, 1 << logn, 0)
+            assert (c, glv) == (c_exp, 0) and c * W >= 256 and W == -(-256 // c) and nb == W << (c - 1)
+            if logn != 22:
+                assert c == work_model(1 << logn, g)[0]
+        for logn in (16, 18, 20):
+            assert _plan(eng, g, 1 << logn, -1)[:3] == (16, 9, 2)
+        for logn in (23, 24, 26):
+            assert _plan(eng, g, 1 << logn, -1)[2] == 0
+        # forced GLV: a width dividing 128 has 128/c + 1 windows, any other keeps the carry window (c·W ≥ 129)
+        c, W, glv, _ = _plan(eng, g, 1 << 12, 1)
+        assert glv in (1, 2) and (W == 128 // c + 1 if 128 % c == 0 else c * W >= 129)
+    out = (ctypes.c_int * 4)()
+    assert eng._lib.lib.b200msm_plan_query(7, 1024, 0, out) != 0
+    assert eng._lib.lib.b200msm_plan_query(0, 0, 0, out) != 0
+
+
+def test_table_plan_host_logic(eng):
+    """fixed-base table widths: only those whose top window keeps ≥ c − 5 bits (10, 13, 16, 20), wide
+    enough to fill the GPU from 2^18 points (G1), and windows × points below 2^31"""
+    for g in (0, 1):
+        for logn in range(8, 27):
+            c, W = eng.table_plan(g, 1 << logn)
+            assert c in (10, 13, 16, 20) and W == -(-256 // c)
+            assert 255 - (W - 1) * c >= c - 5
+        assert eng.table_plan(g, 1 << 20) == (20, 13)
+    assert eng.table_plan(0, 1 << 18)[0] == 20
+    with pytest.raises(eng._lib.B200MsmError):
+        eng.table_plan(0, 1 << 28)
+    with pytest.raises(eng._lib.B200MsmError):
+        eng.table_plan(0, 1 << 20, 24)
+    assert eng.table_plan(0, 1000, 11) == (11, 24)   # an explicit width is taken as given
