@@ -1,0 +1,109 @@
+// Planning of one MSM pass: window width, window count, GLV on/off — pure host arithmetic, no
+// CUDA types, so it is unit-tested without a device (tests/cpp/test_plan.cpp, tests/test_abi.py).
+// Replaces SingleMultiexpKernel::calc_window_size (reference src/gpu.rs:218-223: w = ⌈log2 n⌉ − 3
+// clamped to 10 because its kernel keeps the buckets of every thread in global memory).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+
+namespace b200msm {
+
+struct Plan {
+    int c = 0, nwin = 0;
+    bool glv = false;          // split every scalar into two 128-bit halves (k1 + k2·λ) over P and φ(P) = (β·x, y)
+    bool split = false;        // GLV with c | 128: unsigned top digit spread over the last two windows (k_hist)
+    uint32_t nbw = 0, nb = 0;  // buckets per window, total
+};
+
+// Windows of a plan. Plain: c·W ≥ 256 so the top Booth carry stays inside. GLV halves are below
+// 2^128: when c divides 128 their top c bits are taken unsigned (digit ≤ 2^c → two windows' worth
+// of buckets, no carry window); otherwise c·W ≥ 129 as for the plain plan.
+inline int plan_windows(bool glv, int c, bool *split) {
+    *split = glv && 128 % c == 0;
+    if (!glv) return (256 + c - 1) / c;
+    return *split ? 128 / c + 1 : (129 + c - 1) / c;
+}
+
+// Window width and GLV choice from a time model fitted to the measured phases on B200 (µs):
+// accumulation at 88 % (G1) / 76 % (G2) of the 18.5 T IMAD/s pipe, the fan-in-32 reduction level
+// at 55 %, 3.4 µs (G1) / 11 µs (G2) per dependent doubling of the Horner chain, 23 ps per sorted
+// entry.  Without GLV this lands on the work-minimising c* of SURVEY §8(d) (13/16/18/20 at
+// 2^16/20/22/24) — the width the roofline numerator assumes.
+inline double plan_time_us(size_t n, bool g2, bool glv, int c) {
+    bool split;
+    const double W = plan_windows(glv, c, &split), entries = (glv ? 2.0 : 1.0) * (double)n;
+    const double Wacc = split ? W - 1 : W;  // an entry lands in one of the two top windows
+    const double madd = g2 ? 28 : 10, add = g2 ? 40 : 14, pipe = 18.5e6;  // IMAD per µs
+    // one thread per bucket: below ≈2.5 warps per scheduler (4 × 148 of them) the dependent-issue latency of the
+    // product chain shows (measured with 2^15 buckets: 0.6 of the pipe)
+    // (GLV: the φ(P) entries read x from the β·x table and y from the base record — measured 2.5 % / 6 % slower)
+    const double wps = W * std::pow(2.0, c - 1) / 32 / 592;
+    const double eff = std::min(g2 ? 0.76 : 0.88, 0.35 * wps) * (glv ? (g2 ? 0.94 : 0.975) : 1.0);
+    double t = entries * Wacc * madd * 588 / (pipe * eff);
+    t += W * std::pow(2.0, c - 1) * 2 * add * 588 / (pipe * 0.55);
+    t += (split ? (W - 2) * c + c - 1 : (W - 1) * c) * (g2 ? 11.0 : 3.4) + 250;
+    t += entries * W * 2.3e-5;
+    if (glv) {
+        t += (double)n * (g2 ? 2 : 1) * 588 / (pipe * 0.5) + (double)n * 4e-5;  // β·x table, decomposition
+        // a top window with few bits piles its entries into few buckets: block-cooperative path, ≈3.5× the cost
+        // The halves are below λ ≈ 0.673·2^128, so the top window only uses ⌊λ / 2^(c(W−1))⌋ + 1 of its buckets.
+        // When that is few, its entries pile up past the heavy-bucket threshold and go down the block-cooperative
+        // path (and serialise the grouping's atomics): never pick such a width.
+        const int shift = c * ((int)W - 1);
+        const double top_buckets = std::floor(0.673 * std::pow(2.0, 128 - shift)) + 1;
+        const double thr = std::max(std::max(32.0, 3 * entries / std::pow(2.0, c - 1)), entries * W / 175000);
+        if (!split && entries / top_buckets > 0.7 * thr) t += 1e5;
+    }
+    return t;
+}
+inline void auto_plan(size_t n, bool g2, int glv_mode, int c_override, Plan &pl) {
+    double best = 1e300;
+    for (int glv = 0; glv <= 1; glv++) {
+        if (glv_mode == 0 && glv) continue;
+        if (glv_mode == 1 && !glv) continue;
+        if (glv && glv_mode < 0 && n > (1u << 22)) continue;  // automatic choice only where it was measured to pay
+        if (glv && 2 * n >= (1ull << 31)) continue;
+        for (int c = 2; c <= 22; c++) {
+            if (c_override > 0 && c != c_override) continue;
+            double t = plan_time_us(n, g2, glv, c);
+            if (t < best) { best = t; pl.c = c; pl.glv = glv; }
+        }
+    }
+    pl.nwin = plan_windows(pl.glv, pl.c, &pl.split);
+    pl.nbw = 1u << (pl.c - 1);
+    pl.nb = pl.nbw * (uint32_t)pl.nwin;
+}
+inline int auto_window(size_t n, bool g2) {  // non-GLV width (scratch estimates)
+    Plan pl;
+    auto_plan(n, g2, 0, 0, pl);
+    return pl.c;
+}
+
+// Fixed-base window table (table[w][i] = 2^(c·w)·P_i): one bucket set for all windows, no Horner
+// chain, so the width only trades the n·W additions of the accumulation against one window's
+// bucket reduction (+ a log-depth tree) — wider than the plain plan's at every n.
+inline int table_plan(size_t n, bool g2) {
+    const double madd = g2 ? 28 : 10, add = g2 ? 40 : 14, pipe = 18.5e6;
+    double best = 1e300;
+    int bc = 10;
+    for (int c = 10; c <= 23; c++) {           // W ≤ 26: the table stays within 26× the bases
+        const double W = std::ceil(256.0 / c);
+        // one thread per bucket and only 2^(c−1) buckets in all: below ≈2.5 warps per scheduler (4 × 148 of them)
+        // the dependent-issue latency of the product chain shows (measured: c = 16 → 0.6 of the pipe)
+        const double wps = std::pow(2.0, c - 1) / 32 / 592, eff = std::min(g2 ? 0.76 : 0.88, 0.35 * wps);
+        double t = (double)n * W * madd * 588 / (pipe * eff) + std::pow(2.0, c - 1) * 2 * add * 588 / (pipe * 0.55) +
+                   (double)n * W * 2.3e-5 + c * (g2 ? 40.0 : 16.0);
+        // the top window only holds 255 − (W−1)·c bits: when that is few, its n entries pile into a
+        // handful of buckets and go down the block-cooperative path (≈3.5× the cost per entry)
+        const int topbits = std::max(0, 255 - ((int)W - 1) * c);
+        const double m = (double)n * W, thr = std::max(std::max(32.0, 4 * m / std::pow(2.0, c - 1)), m / 175000);
+        if (topbits < c - 1 && (double)n / std::pow(2.0, topbits) > thr) t += (double)n * madd * 588 / pipe * 3.5;
+        if (topbits < c - 5) t += 1e4;  // … and their counters serialise the grouping's atomics: never pick such a width
+        if (t < best) { best = t; bc = c; }
+    }
+    return bc;
+}
+
+}  // namespace b200msm

@@ -1,0 +1,45 @@
+// Host-only unit test of the planner (ark_blst_b200/csrc/plan.h): compiled with g++, no CUDA.
+// The plain plan must keep every scalar bit plus the Booth carry inside its windows and land on
+// the work-minimising c* of SURVEY §8(d) at the BASELINE sizes; GLV plans must cover 128-bit
+// halves; table plans must only use widths whose top window is not degenerate.
+#include <cstdio>
+
+#include "../../ark_blst_b200/csrc/plan.h"
+
+using namespace b200msm;
+static int failures = 0;
+#define CHECK(c) do { if (!(c)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); failures++; } } while (0)
+
+int main() {
+    for (int g2 = 0; g2 < 2; g2++) {
+        for (int logn = 1; logn <= 27; logn++) {
+            for (int mode = -1; mode <= 1; mode++) {
+                Plan p;
+                auto_plan((size_t)1 << logn, g2, mode, 0, p);
+                CHECK(p.c >= 2 && p.c <= 22 && p.nwin >= 1);
+                CHECK(p.nbw == 1u << (p.c - 1) && p.nb == p.nbw * (uint32_t)p.nwin);
+                if (!p.glv) CHECK(p.c * p.nwin >= 256 && (p.nwin - 1) * p.c < 256);
+                else if (p.split) CHECK(128 % p.c == 0 && p.nwin == 128 / p.c + 1);
+                else CHECK(p.c * p.nwin >= 129 && (p.nwin - 1) * p.c < 129);
+                if (mode == 0) CHECK(!p.glv);
+                if (mode == 1) CHECK(p.glv);
+                if (mode == -1 && logn > 22) CHECK(!p.glv);
+            }
+            for (int c = 2; c <= 22; c++) {  // an explicit width is honoured
+                Plan p;
+                auto_plan((size_t)1 << logn, g2, 0, c, p);
+                CHECK(p.c == c && !p.glv);
+            }
+            int tc = table_plan((size_t)1 << logn, g2);
+            int tw = (256 + tc - 1) / tc;
+            CHECK((tc == 10 || tc == 13 || tc == 16 || tc == 20) && 255 - (tw - 1) * tc >= tc - 5);
+        }
+        Plan p;
+        auto_plan(1u << 16, g2, 0, 0, p); CHECK(p.c == 13 && p.nwin == 20);
+        auto_plan(1u << 20, g2, 0, 0, p); CHECK(p.c == 16 && p.nwin == 16);
+        auto_plan(1u << 24, g2, 0, 0, p); CHECK(p.c == 20 && p.nwin == 13);
+        auto_plan(1u << 20, g2, -1, 0, p); CHECK(p.glv && p.split && p.c == 16 && p.nwin == 9);
+    }
+    std::printf(failures ? "FAILED (%d)\n" : "ok\n", failures);
+    return failures ? 1 : 0;
+}

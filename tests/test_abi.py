@@ -140,3 +140,11 @@ def test_table_plan_host_logic(eng):
     with pytest.raises(eng._lib.B200MsmError):
         eng.table_plan(0, 1 << 20, 24)
     assert eng.table_plan(0, 1000, 11) == (11, 24)   # an explicit width is taken as given
+
+
+def test_planner_cpp_unit(tmp_path):
+    """tests/cpp/test_plan.cpp: the planner header compiled with plain g++ (no CUDA, no device)"""
+    exe = str(tmp_path / "test_plan")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_plan.cpp")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
