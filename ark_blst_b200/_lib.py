@@ -45,6 +45,8 @@ SIGNATURES = {
     "b200msm_set_glv": (ctypes.c_int, [ctypes.c_int]),
     "b200msm_set_heavy_factor": (ctypes.c_int, [ctypes.c_int]),
     "b200msm_set_lane": (ctypes.c_int, [ctypes.c_int]),
+    "b200msm_host_register": (ctypes.c_int, [vp, ctypes.c_size_t]),
+    "b200msm_host_unregister": (ctypes.c_int, [vp]),
     "b200msm_set_stream_slices": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t]),
     "b200msm_set_max_chunk": (ctypes.c_int, [ctypes.c_size_t]),
     "b200msm_set_profiling": (ctypes.c_int, [ctypes.c_int]),

@@ -520,6 +520,11 @@ int msm_streamed(int group, DeviceCtx &cx, const void *h_bases, const void *d_re
     if (cx.busy_valid) CUDA_TRY(cudaStreamWaitEvent(cx.stream, cx.ev_busy, 0));
     // the previous call's kernels may still read cx.scalars / cx.bases: copies wait for them too
     if (cx.busy_valid) CUDA_TRY(cudaStreamWaitEvent(cx.copy_stream, cx.ev_busy, 0));
+    const char *dev_bases = h_bases ? (const char *)cx.bases.p : (const char *)d_resident;
+    // Copies and kernels of slice k are issued together, slice after slice: with pinned host memory
+    // everything is asynchronous anyway; with ordinary pageable memory (a Rust Vec) cudaMemcpyAsync
+    // stages through the driver and blocks the host, and this order keeps the GPU accumulating
+    // slice k while the host is stuck copying slice k+1 (19.5 → 13.7 ms at G1 2^20 one-shot).
     for (int k = 0; k < K; k++) {
         const size_t lo = n * k / K, hi = n * (k + 1) / K;
         cudaMemcpyAsync((char *)cx.scalars.p + lo * 32, h_scalars + 4 * lo, (hi - lo) * 32, cudaMemcpyHostToDevice, cx.copy_stream);
@@ -528,10 +533,6 @@ int msm_streamed(int group, DeviceCtx &cx, const void *h_bases, const void *d_re
             cudaMemcpyAsync((char *)cx.bases.p + lo * AB, (const char *)h_bases + lo * AB, (hi - lo) * AB, cudaMemcpyHostToDevice, cx.copy_stream);
             cudaEventRecord(cx.ev_slice[2 * k + 1], cx.copy_stream);
         }
-    }
-    const char *dev_bases = h_bases ? (const char *)cx.bases.p : (const char *)d_resident;
-    for (int k = 0; k < K; k++) {
-        const size_t lo = n * k / K, hi = n * (k + 1) / K;
         PassOpts po;
         po.plan = &pl;
         po.into = k > 0;
@@ -926,6 +927,16 @@ int b200msm_set_stream_slices(int slices, size_t min_points) {
     if (slices < 1 || slices > 8) return fail(B200MSM_EINVAL, "stream slices must be 1 (off) .. 8");
     g_eng.stream_slices = slices;
     g_eng.stream_min = min_points ? min_points : (size_t)1 << 18;
+    return 0;
+}
+int b200msm_host_register(const void *ptr, size_t bytes) {
+    if (!ptr || !bytes) return fail(B200MSM_EINVAL, "null pointer");
+    CUDA_TRY(cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterPortable));
+    return 0;
+}
+int b200msm_host_unregister(const void *ptr) {
+    if (!ptr) return fail(B200MSM_EINVAL, "null pointer");
+    CUDA_TRY(cudaHostUnregister(const_cast<void *>(ptr)));
     return 0;
 }
 int b200msm_set_lane(int lane) {

@@ -138,6 +138,12 @@ int b200msm_set_window_bits(int c);
  * number of bucket additions. -1 = automatic (time model; the default: on for n ≤ 2^22), 0 = never,
  * 1 = always. Results are the same group elements either way. */
 int b200msm_set_glv(int mode);
+/* Page-lock a caller-owned host buffer (a long-lived scalar or base array) so that the host-buffer
+ * entry points copy from it asynchronously at full PCIe rate: ordinary pageable memory is staged
+ * by the driver at about a fifth of that and blocks the calling thread (G1 2^20 one-shot: 8.3 ms
+ * from pinned, 13.7 ms from pageable memory; with resident bases 8.0 vs 8.2 ms).  Thin wrappers of cudaHostRegister / Unregister. */
+int b200msm_host_register(const void *ptr, size_t bytes);
+int b200msm_host_unregister(const void *ptr);
 /* Lanes: the device-pointer entry points called by THIS host thread use context `lane` (0..7,
  * default 0) of the current device — its own scratch arena, created on first use.  MSMs issued
  * on different lanes and different streams overlap: the latency-bound reduction/combination of

@@ -21,6 +21,13 @@ for spec in sys.argv[1:]:
     hs = torch.empty((n, 4), dtype=torch.int64, pin_memory=True); hs.copy_(scalars)
     torch.cuda.synchronize()
     hb_np, hs_np = hb.numpy().view(np.uint64), hs.numpy().view(np.uint64)
+    import os
+    if os.environ.get("PAGEABLE"):   # ordinary (pageable) host memory, as a Rust Vec would be
+        hb_np, hs_np = hb_np.copy(), hs_np.copy()
+        if os.environ.get("PAGEABLE") == "register":   # ... then page-locked in place through the library
+            L.b200msm_init(-1, 1)
+            assert L.b200msm_host_register(hb_np.ctypes.data, hb_np.nbytes) == 0
+            assert L.b200msm_host_register(hs_np.ctypes.data, hs_np.nbytes) == 0
     grp = eng.G2Projective if g2 else eng.G1Projective
     exp = cref.msm_by_dlog(g2, 1, cref.synth_scalars(2, n, False))
     res = {}
@@ -30,4 +37,16 @@ for spec in sys.argv[1:]:
         t0 = time.perf_counter()
         for _ in range(10): out = grp.msm(hb_np, hs_np)
         res[slices] = {"ms": round((time.perf_counter() - t0) * 100, 3), "parity": bool(cref.affine_equal(g2, out, exp))}
-    print(json.dumps({"group": g, "logn": int(logn), "e2e_by_slices": res}), flush=True)
+    rb = eng.ResidentBases(grp, hb_np)
+    for _ in range(3): out = rb.msm(hs_np)
+    t0 = time.perf_counter()
+    for _ in range(10): out = rb.msm(hs_np)
+    res_ms = round((time.perf_counter() - t0) * 100, 3)
+    rb.precompute()
+    for _ in range(3): out = rb.msm(hs_np)
+    t0 = time.perf_counter()
+    for _ in range(10): out = rb.msm(hs_np)
+    tbl_ms = round((time.perf_counter() - t0) * 100, 3)
+    rb.close()
+    print(json.dumps({"group": g, "logn": int(logn), "pageable": bool(os.environ.get("PAGEABLE")), "e2e_by_slices": res,
+                      "resident_ms": res_ms, "resident_table_ms": tbl_ms, "table_parity": bool(cref.affine_equal(g2, out, exp))}), flush=True)
