@@ -26,6 +26,26 @@ extern "C" {
     fn b200msm_bases_precompute(handle: *mut core::ffi::c_void, window_bits: c_int) -> c_int;
     fn b200msm_run(handle: *const core::ffi::c_void, scalars: *const u64, n: usize, scalars_are_montgomery: c_int, out: *mut u64) -> c_int;
     fn b200msm_bases_free(handle: *mut core::ffi::c_void) -> c_int;
+    // page-lock a long-lived host buffer (a Vec is pageable memory: the driver stages it at a fraction of the PCIe rate)
+    fn b200msm_host_register(ptr: *const core::ffi::c_void, bytes: usize) -> c_int;
+    fn b200msm_host_unregister(ptr: *const core::ffi::c_void) -> c_int;
+}
+
+/// Page-locks `buf` for as long as the guard lives, so `msm` copies from it at full PCIe rate.
+pub struct Pinned<'a, T>(&'a [T]);
+impl<'a, T> Pinned<'a, T> {
+    pub fn new(buf: &'a [T]) -> Result<Self, usize> {
+        let rc = unsafe { b200msm_host_register(buf.as_ptr() as *const _, core::mem::size_of_val(buf)) };
+        if rc != 0 { Err(0) } else { Ok(Self(buf)) }
+    }
+    pub fn as_slice(&self) -> &'a [T] {
+        self.0
+    }
+}
+impl<T> Drop for Pinned<'_, T> {
+    fn drop(&mut self) {
+        unsafe { b200msm_host_unregister(self.0.as_ptr() as *const _) };
+    }
 }
 
 // The casts below are sound only because every wrapper is #[repr(transparent)] over the blst type
