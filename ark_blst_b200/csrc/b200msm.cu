@@ -35,6 +35,7 @@ int fail(int code, const std::string &msg) {
 #define CUDA_TRY(expr)                                                                       \
     do {                                                                                     \
         cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess) cudaGetLastError(); /* do not leave it for the next call's check */ \
         if (e__ != cudaSuccess)                                                              \
             return fail(e__ == cudaErrorMemoryAllocation ? B200MSM_ENOMEM : B200MSM_ECUDA,   \
                         std::string(#expr) + ": " + cudaGetErrorString(e__));                \

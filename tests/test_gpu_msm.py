@@ -280,3 +280,24 @@ def test_streamed_host_msm(eng, cref, g2, n, slices):
         L.b200msm_set_glv(-1)
         L.b200msm_set_stream_slices(8, 0)
 
+
+
+def test_host_register_roundtrip(eng, cref):
+    """b200msm_host_register page-locks the caller's (pageable) numpy buffers in place; results are
+    unchanged, unregistering twice is an error status, never a crash"""
+    L = eng._lib.lib
+    n = 4000
+    bases = cref.synth_bases(0, 321, n).copy()
+    sc = cref.synth_scalars(322, n, True).copy()
+    exp = cref.msm(0, bases, sc, 1)
+    assert L.b200msm_init(-1, 1) == 0
+    assert L.b200msm_host_register(bases.ctypes.data, bases.nbytes) == 0
+    assert L.b200msm_host_register(sc.ctypes.data, sc.nbytes) == 0
+    try:
+        assert cref.affine_equal(0, eng.G1Projective.msm(bases, sc), exp)
+    finally:
+        assert L.b200msm_host_unregister(bases.ctypes.data) == 0
+        assert L.b200msm_host_unregister(sc.ctypes.data) == 0
+    assert L.b200msm_host_unregister(sc.ctypes.data) != 0
+    assert L.b200msm_host_register(None, 16) != 0
+    assert cref.affine_equal(0, eng.G1Projective.msm(bases, sc), exp)
