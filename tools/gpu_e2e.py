@@ -38,11 +38,29 @@ for spec in sys.argv[1:]:
         for _ in range(10): out = grp.msm(hb_np, hs_np)
         res[slices] = {"ms": round((time.perf_counter() - t0) * 100, 3), "parity": bool(cref.affine_equal(g2, out, exp))}
     rb = eng.ResidentBases(grp, hb_np)
+    by_slices = {}
+    for slices in (1, 2, 4, 8):
+        L.b200msm_set_stream_slices(slices, 1 if slices > 1 else 0)
+        for _ in range(3): out = rb.msm(hs_np)
+        t0 = time.perf_counter()
+        for _ in range(10): out = rb.msm(hs_np)
+        by_slices[slices] = round((time.perf_counter() - t0) * 100, 3)
+    print(json.dumps({"resident_by_slices": by_slices}), flush=True)
+    L.b200msm_set_stream_slices(8, 0)
     for _ in range(3): out = rb.msm(hs_np)
     t0 = time.perf_counter()
     for _ in range(10): out = rb.msm(hs_np)
     res_ms = round((time.perf_counter() - t0) * 100, 3)
     rb.precompute()
+    by_slices = {}
+    for slices in (1, 2, 4, 8):
+        L.b200msm_set_stream_slices(slices, 1 if slices > 1 else 0)
+        for _ in range(3): out = rb.msm(hs_np)
+        t0 = time.perf_counter()
+        for _ in range(10): out = rb.msm(hs_np)
+        by_slices[slices] = round((time.perf_counter() - t0) * 100, 3)
+    print(json.dumps({"table_by_slices": by_slices}), flush=True)
+    L.b200msm_set_stream_slices(8, 0)
     for _ in range(3): out = rb.msm(hs_np)
     t0 = time.perf_counter()
     for _ in range(10): out = rb.msm(hs_np)
