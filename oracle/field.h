@@ -46,7 +46,35 @@ static inline int fp_eq(const fp_t *a, const fp_t *b) {
     for (int i = 0; i < 6; i++) t |= a->l[i] ^ b->l[i];
     return t == 0;
 }
-/* r = a - p if a >= p */
+/* r = a - p if a >= p  (hi = carry-out word of a).  add / sub / final subtraction go through the
+ * compiler's carry-flag builtins on x86-64 (adc / sbb chains, as blst's add_mod_384 / sub_mod_384
+ * assembly has them); the u128 forms are the portable fallback */
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <x86intrin.h>
+static inline void fp_cond_sub_p(fp_t *r, const uint64_t a[6], uint64_t hi) {
+    unsigned long long t[6];
+    unsigned char brw = 0;
+    for (int i = 0; i < 6; i++) brw = _subborrow_u64(brw, a[i], FP_P.l[i], &t[i]);
+    /* take t when no final borrow, or when the carry-out word `hi` absorbs it */
+    uint64_t keep = (uint64_t)0 - (uint64_t)((hi == 0) & brw);
+    for (int i = 0; i < 6; i++) r->l[i] = (a[i] & keep) | (t[i] & ~keep);
+}
+static inline void fp_add(fp_t *r, const fp_t *a, const fp_t *b) {
+    unsigned long long t[6];
+    unsigned char c = 0;
+    for (int i = 0; i < 6; i++) c = _addcarry_u64(c, a->l[i], b->l[i], &t[i]);
+    fp_cond_sub_p(r, (const uint64_t *)t, c);
+}
+static inline void fp_sub(fp_t *r, const fp_t *a, const fp_t *b) {
+    unsigned long long t[6];
+    unsigned char brw = 0;
+    for (int i = 0; i < 6; i++) brw = _subborrow_u64(brw, a->l[i], b->l[i], &t[i]);
+    uint64_t mask = (uint64_t)0 - (uint64_t)brw;
+    unsigned char c = 0;
+    for (int i = 0; i < 6; i++) c = _addcarry_u64(c, t[i], FP_P.l[i] & mask, &t[i]);
+    for (int i = 0; i < 6; i++) r->l[i] = t[i];
+}
+#else
 static inline void fp_cond_sub_p(fp_t *r, const uint64_t a[6], uint64_t hi) {
     uint64_t t[6];
     u128 brw = 0;
@@ -55,7 +83,6 @@ static inline void fp_cond_sub_p(fp_t *r, const uint64_t a[6], uint64_t hi) {
         t[i] = (uint64_t)d;
         brw = (d >> 64) & 1;
     }
-    /* take t when no final borrow, or when the carry-out word `hi` absorbs it */
     int use_t = (hi != 0) || (brw == 0);
     for (int i = 0; i < 6; i++) r->l[i] = use_t ? t[i] : a[i];
 }
@@ -87,6 +114,7 @@ static inline void fp_sub(fp_t *r, const fp_t *a, const fp_t *b) {
     }
     memcpy(r->l, t, sizeof t);
 }
+#endif
 static inline void fp_neg(fp_t *r, const fp_t *a) {
     if (fp_is_zero(a)) { *r = *a; return; }
     fp_t z = {{0}};
@@ -94,8 +122,8 @@ static inline void fp_neg(fp_t *r, const fp_t *a) {
 }
 static inline void fp_dbl(fp_t *r, const fp_t *a) { fp_add(r, a, a); }
 
-/* Montgomery product a·b·2^-384 mod p, CIOS over 64-bit limbs */
-static inline void fp_mul(fp_t *r, const fp_t *a, const fp_t *b) {
+/* Montgomery product a·b·2^-384 mod p, CIOS over 64-bit limbs — portable form */
+static inline void fp_mul_portable(fp_t *r, const fp_t *a, const fp_t *b) {
     uint64_t t[8] = {0};
     for (int i = 0; i < 6; i++) {
         u128 c = 0;
@@ -119,6 +147,75 @@ static inline void fp_mul(fp_t *r, const fp_t *a, const fp_t *b) {
         t[6] = t[7] + (uint64_t)(c >> 64);
     }
     fp_cond_sub_p(r, t, t[6]);
+}
+
+/* The same product with MULX and the two independent ADCX / ADOX carry chains — the instruction
+ * mix of blst's mulx_mont_384 (the x86-64 path blst =0.3.10 takes on a CPU with ADX + BMI2;
+ * restated, not copied: blst is not vendored in the reference).  One row = t += a·b_i on the two
+ * chains, then m = t0·(−p⁻¹), t += m·p, and the window slides down one limb by renaming registers.
+ * p < 2^381 leaves the top limb's high bits clear, so a row never carries out of t6.
+ * Chosen at run time (fp_mul below); limb-for-limb equal to fp_mul_portable (tests/test_oracle.py). */
+#if defined(__x86_64__) && defined(__GNUC__)
+#define FP_HAVE_ADX_PATH 1
+#define FP_ADX_ROW(T0, T1, T2, T3, T4, T5, T6, SRC, MULT)                                   \
+    __asm__("xorl %%eax, %%eax\n\t"              /* rax = 0, CF = OF = 0 */                  \
+            "mulx 0(%[s]), %[lo], %[ha]\n\t"                                                 \
+            "adcx %[lo], %[t0]\n\t"                                                          \
+            "mulx 8(%[s]), %[lo], %[hb]\n\t"                                                 \
+            "adox %[ha], %[t1]\n\t"                                                          \
+            "adcx %[lo], %[t1]\n\t"                                                          \
+            "mulx 16(%[s]), %[lo], %[ha]\n\t"                                                \
+            "adox %[hb], %[t2]\n\t"                                                          \
+            "adcx %[lo], %[t2]\n\t"                                                          \
+            "mulx 24(%[s]), %[lo], %[hb]\n\t"                                                \
+            "adox %[ha], %[t3]\n\t"                                                          \
+            "adcx %[lo], %[t3]\n\t"                                                          \
+            "mulx 32(%[s]), %[lo], %[ha]\n\t"                                                \
+            "adox %[hb], %[t4]\n\t"                                                          \
+            "adcx %[lo], %[t4]\n\t"                                                          \
+            "mulx 40(%[s]), %[lo], %[hb]\n\t"                                                \
+            "adox %[ha], %[t5]\n\t"                                                          \
+            "adcx %[lo], %[t5]\n\t"                                                          \
+            "adox %[hb], %[t6]\n\t"                                                          \
+            "adcx %%rax, %[t6]\n\t"                                                          \
+            : [t0] "+r"(T0), [t1] "+r"(T1), [t2] "+r"(T2), [t3] "+r"(T3), [t4] "+r"(T4),     \
+              [t5] "+r"(T5), [t6] "+r"(T6), [lo] "=&r"(lo_), [ha] "=&r"(ha_), [hb] "=&r"(hb_) \
+            : [s] "r"(SRC), "d"(MULT), "m"(*(const uint64_t(*)[6])(SRC))                    \
+            : "rax", "cc")
+static inline void fp_mul_adx(fp_t *r, const fp_t *a, const fp_t *b) {
+    uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7, lo_, ha_, hb_;
+    const uint64_t *pa = a->l, *pp = FP_P.l;
+#define FP_ADX_STEP(A0, A1, A2, A3, A4, A5, A6, A7, BI)           \
+    FP_ADX_ROW(A0, A1, A2, A3, A4, A5, A6, pa, BI);               \
+    A7 = 0;                                                       \
+    FP_ADX_ROW(A0, A1, A2, A3, A4, A5, A6, pp, A0 * FP_PINV)      /* A0 is now 0: the window is A1..A6, A7 = 0 */
+    FP_ADX_STEP(t0, t1, t2, t3, t4, t5, t6, t7, b->l[0]);
+    FP_ADX_STEP(t1, t2, t3, t4, t5, t6, t7, t0, b->l[1]);
+    FP_ADX_STEP(t2, t3, t4, t5, t6, t7, t0, t1, b->l[2]);
+    FP_ADX_STEP(t3, t4, t5, t6, t7, t0, t1, t2, b->l[3]);
+    FP_ADX_STEP(t4, t5, t6, t7, t0, t1, t2, t3, b->l[4]);
+    FP_ADX_STEP(t5, t6, t7, t0, t1, t2, t3, t4, b->l[5]);
+#undef FP_ADX_STEP
+    uint64_t t[6] = {t6, t7, t0, t1, t2, t3};
+    fp_cond_sub_p(r, t, t4);
+}
+static int fp_adx_state = -1; /* -1 unknown, 0 portable, 1 ADX */
+static inline int fp_use_adx(void) {
+    if (__builtin_expect(fp_adx_state < 0, 0)) {
+        __builtin_cpu_init();
+        fp_adx_state = __builtin_cpu_supports("adx") && __builtin_cpu_supports("bmi2");
+    }
+    return fp_adx_state;
+}
+#else
+#define FP_HAVE_ADX_PATH 0
+static int fp_adx_state = 0;
+static inline int fp_use_adx(void) { return 0; }
+static inline void fp_mul_adx(fp_t *r, const fp_t *a, const fp_t *b) { fp_mul_portable(r, a, b); }
+#endif
+static inline void fp_mul(fp_t *r, const fp_t *a, const fp_t *b) {
+    if (fp_use_adx()) fp_mul_adx(r, a, b);
+    else fp_mul_portable(r, a, b);
 }
 static inline void fp_sqr(fp_t *r, const fp_t *a) { fp_mul(r, a, a); }
 static inline void fp_to_mont(fp_t *r, const fp_t *a) { fp_mul(r, a, &FP_R2); }

@@ -76,6 +76,41 @@ static unsigned window_rule(size_t n) {
     return wbits > 12 ? wbits - 3 : wbits > 4 ? wbits - 2 : wbits ? 2 : 1;
 }
 
+/* blst's `breakdown(nbits, window, ncpus) -> (nx, ny, wnd)` [UPSTREAM-KNOWLEDGE: blst 0.3.10
+ * bindings/rust/src/pippenger.rs, restated from its published logic; blst is not vendored in the
+ * reference].  Few CPUs: one slice, the window nudged so the windows divide over the CPUs; many
+ * CPUs: nx slices with the window narrowed by num_bits(3·nx/2). */
+static unsigned num_bits(size_t l) {
+    unsigned b = 0;
+    while (l) { b++; l >>= 1; }
+    return b;
+}
+static void breakdown(unsigned nbits, unsigned window, unsigned ncpus, unsigned *pnx, unsigned *pny,
+                      unsigned *pwnd) {
+    unsigned nx, wnd;
+    if (nbits > window * ncpus) {
+        nx = 1;
+        wnd = num_bits(ncpus / 4);
+        if (window + wnd > 18) wnd = window - wnd;
+        else {
+            wnd = (nbits / window + ncpus - 1) / ncpus;
+            wnd = (nbits / (window + 1) + ncpus - 1) / ncpus < wnd ? window + 1 : window;
+        }
+    } else {
+        nx = 2;
+        wnd = window - 2;
+        while ((nbits / wnd + 1) * nx < ncpus) {
+            nx += 1;
+            wnd = window - num_bits(3 * nx / 2);
+        }
+        nx -= 1;
+        wnd = window - num_bits(3 * nx / 2);
+    }
+    unsigned ny = nbits / wnd + 1;
+    wnd = nbits / ny + 1;
+    *pnx = nx; *pny = ny; *pwnd = wnd;
+}
+
 /* ---- shared job description ------------------------------------------------------------- */
 typedef struct {
     int g2;
@@ -152,16 +187,18 @@ static int msm_common(int g2, const void *bases, const uint64_t *scalars, size_t
     J.n = n;
     J.c = window > 0 ? (unsigned)window : window_rule(n);
     if (J.c > 24) J.c = 24;
-    J.nwin = (256 + J.c - 1) / J.c; /* W·c ≥ 256 > 255 = |r| keeps the top Booth carry inside */
-    /* enough tiles to keep every thread busy, but slices no shorter than ~4 bucket-sets */
     J.nslice = 1;
-    if (nthreads > 1) {
-        unsigned want = (unsigned)((2 * nthreads + J.nwin - 1) / J.nwin);
-        size_t maxs = n >> J.c ? n >> J.c : 1;
-        if (want > maxs) want = (unsigned)maxs;
-        if (want < 1) want = 1;
-        J.nslice = want;
+    /* the tile grid of blst's multi-threaded driver (bindings/rust/src/pippenger.rs, `breakdown`):
+     * nx point slices × ny windows, the window narrowed as slices are added so that the bucket
+     * reduction each tile repeats stays in proportion */
+    if (nthreads > 1 && n >= 32 && window <= 0) {
+        unsigned nx, ny, wnd;
+        breakdown(255, J.c, (unsigned)nthreads, &nx, &ny, &wnd);
+        if (wnd < 2) wnd = 2;
+        J.c = wnd;
+        J.nslice = nx;
     }
+    J.nwin = (256 + J.c - 1) / J.c; /* W·c ≥ 256 > 255 = |r| keeps the top Booth carry inside */
     size_t ntile = (size_t)J.nwin * J.nslice;
     size_t xs = g2 ? sizeof(g2_xyzz_t) : sizeof(g1_xyzz_t);
     J.tile_out = malloc(ntile * xs);
@@ -297,6 +334,17 @@ API void ref_fr_from_mont(const uint64_t a[4], uint64_t r[4]) {
 }
 API int ref_booth_digit(const uint64_t s[4], unsigned w, unsigned c) { return booth_digit(s, w, c); }
 API unsigned ref_window_rule(size_t n) { return window_rule(n); }
+API void ref_breakdown(unsigned nbits, unsigned window, unsigned ncpus, unsigned out[3]) {
+    breakdown(nbits, window, ncpus, &out[0], &out[1], &out[2]);
+}
+/* which Montgomery product this build runs on this CPU: 1 = MULX/ADCX/ADOX, 0 = portable u128 */
+API int ref_mul_impl(void) { return fp_use_adx(); }
+API void ref_fp_mul_portable(const uint64_t a[6], const uint64_t b[6], uint64_t r[6]) {
+    fp_mul_portable((fp_t *)r, (const fp_t *)a, (const fp_t *)b);
+}
+API void ref_fp_mul_adx(const uint64_t a[6], const uint64_t b[6], uint64_t r[6]) {
+    fp_mul_adx((fp_t *)r, (const fp_t *)a, (const fp_t *)b);
+}
 
 /* ---- deterministic synthetic inputs (must match oracle/bls12381.py and csrc/synth.cuh) ---- */
 static inline uint64_t splitmix64(uint64_t x) {

@@ -212,3 +212,54 @@ def test_point_encoding_kats_and_roundtrip():
         a = (rng.randrange(o.P), rng.randrange(o.P))
         s = o.fp2_sqrt(o.Fp2Ops.sqr(a))
         assert s is not None and o.Fp2Ops.eq(o.Fp2Ops.sqr(s), o.Fp2Ops.sqr(a))
+
+
+# ---- round 2: the MULX/ADCX/ADOX product (the timed CPU baseline's inner loop) and blst's tile grid ----
+def test_adx_product_equals_portable_and_bigint(cref):
+    """oracle/field.h fp_mul_adx (inline asm, what the timed baseline runs on an ADX+BMI2 host) against the
+    portable u128 product and the big-int oracle, limb for limb, incl. the operands at the edges of [0, p)"""
+    L = cref.lib()
+    rng = random.Random(29)
+    edge = [0, 1, 2, o.P - 1, o.P - 2, (o.P - 1) // 2, o.MONT_R % o.P, o.MONT_RINV, (1 << 380) % o.P, (1 << 64) - 1, 1 << 64]
+    pairs = [(a, b) for a in edge for b in edge] + [(rng.randrange(o.P), rng.randrange(o.P)) for _ in range(500)]
+    for a, b in pairs:
+        A = np.array(o.int_to_limbs(a, 6), dtype=np.uint64)   # raw limbs: the product is a·b·2^-384 of the raw values
+        B = np.array(o.int_to_limbs(b, 6), dtype=np.uint64)
+        want = o.int_to_limbs(a * b * o.MONT_RINV % o.P, 6)
+        assert cref.fp_binop("ref_fp_mul_portable", A, B).tolist() == want
+        if L.ref_mul_impl():
+            assert cref.fp_binop("ref_fp_mul_adx", A, B).tolist() == want
+        assert cref.fp_binop("ref_fp_mul", A, B).tolist() == want
+
+
+def test_blst_tile_grid_restated(cref):
+    """the (slices, windows, width) grid of blst's multi-threaded Pippenger driver as restated in
+    oracle/msm_ref.c `breakdown`: widths cover the 255 scalar bits, and few CPUs never slice"""
+    import ctypes
+
+    L = cref.lib()
+    for cpus in (2, 8, 16, 32, 64, 128, 256):
+        for logn in range(5, 27):
+            out = (ctypes.c_uint * 3)()
+            w = L.ref_window_rule(1 << logn)
+            L.ref_breakdown(255, w, cpus, out)
+            nx, ny, wnd = list(out)
+            assert nx >= 1 and ny * wnd >= 256 and abs(int(wnd) - int(w)) <= 8
+            if 255 > w * cpus:
+                assert nx == 1
+    out = (ctypes.c_uint * 3)()
+    L.ref_breakdown(255, 17, 16, out)          # 2^20 points on the 16-core bench box: 16 full-length tiles of width 16
+    assert list(out) == [1, 16, 16]
+
+
+def test_generator_literals_published():
+    """the standard generators (IETF pairing-friendly-curves draft §4.2.1 / zkcrypto bls12_381), restated
+    literally: pins the oracle's G1_GEN / G2_GEN from outside this repository"""
+    assert o.G1_GEN == (
+        0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB,
+        0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1)
+    assert o.G2_GEN == (
+        (0x024AA2B2F08F0A91260805272DC51051C6E47AD4FA403B02B4510B647AE3D1770BAC0326A805BBEFD48056C8C121BDB8,
+         0x13E02B6052719F607DACD3A088274F65596BD0D09920B61AB5DA61BBDC7F5049334CF11213945D57E5AC7D055D042B7E),
+        (0x0CE5D527727D6E118CC9CDC6DA2E351AADFD9BAA8CBDD3A76D429A695160D12C923AC9CC3BACA289E193548608B82801,
+         0x0606C4A02EA734CC32ACD2B02BC28B99CB3E287E85A763AF267492AB572E99AB3F370D275CEC1DA1AAA9075FF05F79BE))
