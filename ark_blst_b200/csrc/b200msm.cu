@@ -6,13 +6,16 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200msm.h"
@@ -79,7 +82,9 @@ struct DeviceCtx {
     std::mutex mu;
     cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
     cudaEvent_t ev_scalars = nullptr, ev_bases = nullptr, ev_busy = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_share = nullptr;  // this device's share of a sharded MSM is complete (partial delivered to device 0)
     bool busy_valid = false;
+    unsigned fits_epoch = 0;    // Tun::epoch the fit caches below were recorded under
     size_t fits_n[2] = {0, 0};  // largest n per group that already ran as a single pass (arena is big enough)
     size_t fits_tbl_n[2] = {0, 0};  // same for the table path, valid for window width fits_tbl_c
     int fits_tbl_c[2] = {0, 0};
@@ -108,13 +113,10 @@ struct DeviceCtx {
     }
 };
 
-struct Engine {
-    std::mutex mu;
-    bool inited = false;
-    std::vector<std::unique_ptr<DeviceCtx>> ctx;
-    // extra lanes (b200msm_set_lane): further contexts on the same devices with their own scratch, so that MSMs
-    // issued on different streams overlap — one's latency-bound tail under another's accumulation
-    std::vector<std::unique_ptr<DeviceCtx>> lane_ctx;
+// Tunables (the b200msm_set_* calls).  A call takes ONE snapshot when it starts and plans every
+// pass, chunk and slice from it, so a setter racing with running MSMs on other host threads never
+// changes a plan half way through (tests/test_gpu_threads.py flips them under load).
+struct Tun {
     int window_override = 0;
     size_t max_chunk_override = 0;
     int glv_mode = -1;  // -1 automatic (time model; default), 0 never, 1 always
@@ -122,8 +124,50 @@ struct Engine {
     int stream_slices = 8;          // (at most) host-buffer MSMs of ≥ stream_min points per device are uploaded and accumulated in slices
     size_t stream_min = 1u << 18;
     int heavy_factor = 0;  // a bucket is heavy above heavy_factor × the mean occupancy (see run_pass); 0 = automatic
+    int batch_affine = -1; // -1 automatic, 0 never, 1..3 = pairwise batched-affine rounds before the XYZZ accumulation
+    unsigned epoch = 0;    // bumped by every setter that changes what a pass allocates (fit caches are keyed on it)
+};
+struct Share;
+// One persistent host thread per bound device (only when more than one is bound); see msm_host.
+struct DeviceWorker {
+    DeviceCtx *cx = nullptr;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    const Share *job = nullptr;   // set by the caller, cleared by the worker
+    bool quit = false, done = false;
+    int rc = 0;
+    std::string err;
+    void *gather_dst = nullptr;   // device 0's slot for this device's partial
+    int gather_dev = 0;
+    void loop();
+};
+struct Engine {
+    std::mutex mu;
+    bool inited = false;
+    int first = 0;                    // bound device range [first, first + ctx.size())
+    unsigned generation = 0;          // bumped by every (re-)initialisation; resident handles remember theirs
+    std::vector<std::unique_ptr<DeviceCtx>> ctx;
+    // extra lanes (b200msm_set_lane): further contexts on the same devices with their own scratch, so that MSMs
+    // issued on different streams overlap — one's latency-bound tail under another's accumulation
+    std::vector<std::unique_ptr<DeviceCtx>> lane_ctx;
+    // one persistent host thread per bound device when more than one is bound: a sharded host-buffer MSM is
+    // issued on all devices at once instead of device after device from the calling thread
+    std::vector<std::unique_ptr<DeviceWorker>> workers;
+    std::mutex multi_mu;              // one sharded (multi-device) call at a time: they share the gather slots
+    std::mutex tun_mu;
+    Tun tun;
 };
 Engine g_eng;
+Tun tun_snapshot() {
+    std::lock_guard<std::mutex> lk(g_eng.tun_mu);
+    return g_eng.tun;
+}
+template <class Fn> void tun_update(Fn fn, bool replans = true) {
+    std::lock_guard<std::mutex> lk(g_eng.tun_mu);
+    fn(g_eng.tun);
+    if (replans) g_eng.tun.epoch++;
+}
 
 int make_ctx(int d, int lane, int sm_count, std::unique_ptr<DeviceCtx> &out) {
     auto c = std::make_unique<DeviceCtx>();
@@ -138,6 +182,7 @@ int make_ctx(int d, int lane, int sm_count, std::unique_ptr<DeviceCtx> &out) {
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_busy, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_share, cudaEventDisableTiming));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
     int lo_pri = 0, hi_pri = 0;
     CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
@@ -161,11 +206,21 @@ void destroy_ctx(DeviceCtx &c) {
     cudaStreamDestroy(c.copy_stream);
     cudaStreamDestroy(c.aux_stream);
     cudaStreamDestroy(c.tail_stream);
-    for (cudaEvent_t e : {c.ev_scalars, c.ev_bases, c.ev_busy, c.ev_fork, c.ev_join, c.ev_tail_fork, c.ev_tail_join}) cudaEventDestroy(e);
+    for (cudaEvent_t e : {c.ev_scalars, c.ev_bases, c.ev_busy, c.ev_fork, c.ev_join, c.ev_share, c.ev_tail_fork, c.ev_tail_join}) cudaEventDestroy(e);
 }
 
 int engine_init_locked(int first, int ndev) {
-    if (g_eng.inited) return 0;
+    if (g_eng.inited) {
+        // lazy initialisation (first < 0: "whatever is bound") never re-binds; an explicit request for a
+        // different range is an error rather than a silent no-op
+        if (first < 0) return 0;
+        int count = 0;
+        cudaGetDeviceCount(&count);
+        const int want = ndev <= 0 ? count - first : ndev;
+        if (first == g_eng.first && want == (int)g_eng.ctx.size()) return 0;
+        return fail(B200MSM_EINVAL, "engine already bound to devices [" + std::to_string(g_eng.first) + ", " +
+                                        std::to_string(g_eng.first + (int)g_eng.ctx.size()) + "): call b200msm_shutdown before binding another range");
+    }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -176,16 +231,47 @@ int engine_init_locked(int first, int ndev) {
     }
     if (ndev <= 0) ndev = count - first;
     if (first >= count || first + ndev > count) return fail(B200MSM_EINVAL, "device range out of bounds");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    auto undo = [&](int rc) {
+        for (auto &c : g_eng.ctx) destroy_ctx(*c);
+        g_eng.ctx.clear();
+        cudaSetDevice(prev);
+        return rc;
+    };
     for (int d = first; d < first + ndev; d++) {
         cudaDeviceProp p;
-        CUDA_TRY(cudaGetDeviceProperties(&p, d));
+        cudaError_t pe = cudaGetDeviceProperties(&p, d);
+        if (pe != cudaSuccess) return undo(fail(B200MSM_ECUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(pe)));
         if (p.major != 10)
-            return fail(B200MSM_ENODEV, std::string("device ") + std::to_string(d) + " (" + p.name + ") is sm_" +
-                                            std::to_string(p.major * 10 + p.minor) + "; this build is sm_100a only");
+            return undo(fail(B200MSM_ENODEV, std::string("device ") + std::to_string(d) + " (" + p.name + ") is sm_" +
+                                                 std::to_string(p.major * 10 + p.minor) + "; this build is sm_100a only"));
         std::unique_ptr<DeviceCtx> c;
-        if (int rc = make_ctx(d, 0, p.multiProcessorCount, c)) return rc;
+        if (int rc = make_ctx(d, 0, p.multiProcessorCount, c)) return undo(rc);
         g_eng.ctx.push_back(std::move(c));
     }
+    if (ndev > 1) {
+        // partials travel to the first device by peer copy: enable direct access where the topology has it
+        // (NVLink / NVSwitch on an 8×B200 box); without it the copy is staged through the host and still correct
+        for (int d = 1; d < ndev; d++) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, first + d, first) == cudaSuccess && can) {
+                cudaSetDevice(first + d);
+                cudaError_t pe = cudaDeviceEnablePeerAccess(first, 0);
+                if (pe != cudaSuccess) cudaGetLastError();  // already enabled (by torch, say) is fine
+            }
+        }
+        for (int d = 0; d < ndev; d++) {
+            auto w = std::make_unique<DeviceWorker>();
+            w->cx = g_eng.ctx[d].get();
+            DeviceWorker *wp = w.get();
+            w->th = std::thread([wp] { wp->loop(); });
+            g_eng.workers.push_back(std::move(w));
+        }
+    }
+    cudaSetDevice(prev);
+    g_eng.first = first;
+    g_eng.generation++;
     g_eng.inited = true;
     return 0;
 }
@@ -194,14 +280,15 @@ int engine_init(int first, int ndev) {
     return engine_init_locked(first, ndev);
 }
 thread_local int t_lane = 0;
+// context of the calling thread's current device and lane (engine lock held while the lists are walked)
 DeviceCtx *ctx_for_current_device() {
     int d = 0;
     cudaGetDevice(&d);
+    std::lock_guard<std::mutex> lk(g_eng.mu);
     DeviceCtx *base = nullptr;
     for (auto &c : g_eng.ctx)
         if (c->dev == d) base = c.get();
     if (!base || t_lane == 0) return base;
-    std::lock_guard<std::mutex> lk(g_eng.mu);
     for (auto &c : g_eng.lane_ctx)
         if (c->dev == d && c->lane == t_lane) return c.get();
     std::unique_ptr<DeviceCtx> c;
@@ -221,7 +308,7 @@ struct PassOpts {
     const Plan *plan = nullptr;
     bool into = false, finish = true;
 };
-int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scalars_v, size_t n, int mont, void *d_out_v,
+int run_pass(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v, const void *d_scalars_v, size_t n, int mont, void *d_out_v,
               cudaStream_t st, cudaEvent_t bases_ready = nullptr, const TableRef *tbl = nullptr, const PassOpts &po = PassOpts()) {
     if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "group must be B200MSM_G1 or B200MSM_G2");
     const bool g2 = group == B200MSM_G2;
@@ -243,12 +330,12 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
         pl.nbw = 1u << (pl.c - 1);
         pl.nb = pl.nbw;                       // one bucket set shared by all windows
         d_bases = (const uint32_t *)tbl->p;
-    } else auto_plan(n, g2, g_eng.glv_mode, std::min(g_eng.window_override, 22), pl);
+    } else auto_plan(n, g2, tn.glv_mode, tn.window_override, pl);
     const int rwin = tbl ? 1 : pl.nwin;       // windows the reduction sees
     cx.last_plan[0] = pl.c; cx.last_plan[1] = pl.nwin; cx.last_plan[2] = pl.glv ? (pl.split ? 2 : 1) : 0; cx.last_plan[3] = tbl ? 1 : 0;
     const size_t entries = pl.glv ? 2 * n : n;  // per window
     const size_t m = entries * (size_t)pl.nwin;
-    const bool prof = g_eng.profiling;
+    const bool prof = tn.profiling;
     int evi = 0;
     auto mark = [&]() { if (prof) cudaEventRecord(cx.ev[evi++], st); };
 
@@ -271,7 +358,7 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
     // Worst-case list sizes follow from Σ counts = m.
     // (table mode: the buckets the top window also feeds hold up to ≈2.3× the mean, so the factor is 4 there)
     const uint32_t avg = (uint32_t)(((tbl ? m : entries) + pl.nbw - 1) / pl.nbw);
-    const int hfac = g_eng.heavy_factor ? g_eng.heavy_factor : (tbl ? 4 : 3);
+    const int hfac = tn.heavy_factor ? tn.heavy_factor : (tbl ? 4 : 3);
     const uint32_t heavy_thr = std::max<uint32_t>(std::max<uint32_t>(32, (uint32_t)hfac * avg), (uint32_t)(m / 175000));
     const size_t max_heavy = m / (heavy_thr + 1) + 1, max_tasks = m / HEAVY_CHUNK + max_heavy + 1;
     if (int rc = cx.hvy_hdr.reserve(16)) return rc;
@@ -385,7 +472,7 @@ int run_pass(int group, DeviceCtx &cx, const void *d_bases_v, const void *d_scal
 // Scratch bytes one pass over n points needs (sort double buffers dominate).
 size_t pass_scratch_bytes(size_t n, bool g2, int c_override, bool table = false) {
     int c = c_override > 0 ? c_override : auto_window(n, g2);
-    c = std::max(2, std::min(c, 24));
+    c = std::max(2, std::min(c, 22));
     size_t nwin = (256 + c - 1) / c, nb = nwin << (c - 1), m = n * nwin;  // the GLV plan needs about the same
     size_t PB = g2 ? 384 : 192;
     if (table) return m * 8 + (nb / nwin) * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + (64u << 20);
@@ -396,7 +483,7 @@ size_t pass_scratch_bytes(size_t n, bool g2, int c_override, bool table = false)
 // as a TODO (src/gpu.rs:238-239; its calc_chunk_size result is never used, :64-85,114): the points
 // are cut into equal chunks whose sort arrays stay below 2^32 entries and within the free HBM,
 // each chunk yields a Jacobian partial, and the partials are added on the device.
-int run_group(int group, DeviceCtx &cx, const void *d_bases, const void *d_scalars, size_t n, int mont, void *d_out,
+int run_group(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases, const void *d_scalars, size_t n, int mont, void *d_out,
               cudaStream_t st, cudaEvent_t bases_ready = nullptr, const TableRef *tbl = nullptr) {
     if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "group must be B200MSM_G1 or B200MSM_G2");
     const bool g2 = group == B200MSM_G2;
@@ -406,20 +493,24 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases, const void *d_scala
     // not already run as a single pass on this context (the grow-only arena then fits)
     size_t budget = ~(size_t)0;
     const int gi = g2 ? 1 : 0;
+    if (cx.fits_epoch != tn.epoch) {  // a setter changed what a pass of a given size allocates: forget what is known to fit
+        cx.fits_epoch = tn.epoch;
+        cx.fits_n[0] = cx.fits_n[1] = cx.fits_tbl_n[0] = cx.fits_tbl_n[1] = 0;
+    }
     const bool known_fit = tbl ? (tbl->c == cx.fits_tbl_c[gi] && n <= cx.fits_tbl_n[gi]) : n <= cx.fits_n[gi];
-    if (!g_eng.max_chunk_override && !known_fit) {
+    if (!tn.max_chunk_override && !known_fit) {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         budget = (size_t)((double)(free_b + cx.scratch_bytes()) * 0.85);
     }
     size_t chunks = 1;
     auto too_big = [&](size_t cn) {
-        if (g_eng.max_chunk_override) return cn > g_eng.max_chunk_override;
+        if (tn.max_chunk_override) return cn > tn.max_chunk_override;
         if (tbl) return cn * tbl->nwin >= 0xfff00000ull || pass_scratch_bytes(cn, g2, tbl->c, true) > budget;
         Plan p;
-        auto_plan(cn, g2, g_eng.glv_mode, std::min(g_eng.window_override, 22), p);
+        auto_plan(cn, g2, tn.glv_mode, tn.window_override, p);
         size_t ent = (p.glv ? 2 : 1) * cn;
-        return ent * p.nwin >= 0xfff00000ull || cn >= (1ull << 30) || pass_scratch_bytes(cn, g2, g_eng.window_override) > budget;
+        return ent * p.nwin >= 0xfff00000ull || cn >= (1ull << 30) || pass_scratch_bytes(cn, g2, tn.window_override) > budget;
     };
     while (too_big((n + chunks - 1) / chunks)) {
         chunks *= 2;
@@ -427,12 +518,12 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases, const void *d_scala
     }
     int rc = 0;
     if (chunks == 1) {
-        rc = run_pass(group, cx, d_bases, d_scalars, n, mont, d_out, st, bases_ready, tbl);
-        if (!rc && !g_eng.max_chunk_override) {
+        rc = run_pass(group, cx, tn, d_bases, d_scalars, n, mont, d_out, st, bases_ready, tbl);
+        if (!rc && !tn.max_chunk_override) {
             if (tbl) {
                 if (tbl->c != cx.fits_tbl_c[gi]) { cx.fits_tbl_c[gi] = tbl->c; cx.fits_tbl_n[gi] = 0; }
                 cx.fits_tbl_n[gi] = std::max(cx.fits_tbl_n[gi], n);
-            } else if (g_eng.window_override == 0) cx.fits_n[gi] = std::max(cx.fits_n[gi], n);
+            } else cx.fits_n[gi] = std::max(cx.fits_n[gi], n);
         }
     } else {
         const size_t AB = g2 ? 192 : 96, JB = g2 ? 288 : 144;
@@ -441,7 +532,7 @@ int run_group(int group, DeviceCtx &cx, const void *d_bases, const void *d_scala
             size_t lo = n * k / chunks, hi = n * (k + 1) / chunks;
             TableRef sub;
             if (tbl) { sub = *tbl; sub.p = (const char *)tbl->p + lo * AB; }  // same stride, shifted origin
-            rc = run_pass(group, cx, (const char *)d_bases + lo * AB, (const char *)d_scalars + lo * 32, hi - lo, mont,
+            rc = run_pass(group, cx, tn, (const char *)d_bases + lo * AB, (const char *)d_scalars + lo * 32, hi - lo, mont,
                           (char *)cx.chunk_partials.p + k * JB, st, k == 0 ? bases_ready : nullptr, tbl ? &sub : nullptr);
         }
         if (!rc) (g2 ? launch_sum_partials_g2 : launch_sum_partials_g1)((const uint32_t *)cx.chunk_partials.p, (int)chunks, (uint32_t *)d_out, st);
@@ -489,11 +580,16 @@ int msm_host(int group, const uint64_t *bases, const uint64_t *scalars, size_t n
 struct b200msm_bases {
     int group;
     size_t n;
+    unsigned generation = 0;        // engine binding the shards were uploaded under (b200msm_run checks it)
+    std::vector<int> dev;           // CUDA device id per shard: memory is released by these, whatever the engine is bound to by then
     std::vector<DevBuf> shard;      // one per bound device
     std::vector<size_t> lo, cnt;    // index range per device
     // after b200msm_bases_precompute: window-major table per device (window 0 = the shard, which is then released)
     std::vector<DevBuf> table;
     int tbl_c = 0, tbl_nwin = 0;
+    // b200msm_run holds it shared-style (one at a time is enough: the devices serialise anyway),
+    // b200msm_bases_precompute exclusively while it swaps shards for tables
+    mutable std::mutex mu;
 };
 
 namespace {
@@ -503,19 +599,19 @@ namespace {
 // and accumulates slice k into the shared buckets as soon as it has landed — the PCIe transfer
 // of slices 1.. hides behind the accumulation of the slices before them, and the reduction and
 // combination run once.  Result in cx.out; asynchronous.  ctx.mu held, ctx.dev current.
-int msm_streamed(int group, DeviceCtx &cx, const void *h_bases, const void *d_resident, const TableRef *tbl,
+int msm_streamed(int group, DeviceCtx &cx, const Tun &tn, const void *h_bases, const void *d_resident, const TableRef *tbl,
                  const uint64_t *h_scalars, size_t n, int mont) {
     const bool g2 = group == B200MSM_G2;
     const size_t AB = aff_bytes(group);
     // ≈2^17 points per slice (measured best: 2 slices at 2^18, 4 at 2^19, 8 from 2^20 up), unless forced (stream_min < 2^17)
-    const size_t per = std::min<size_t>((size_t)1 << 17, std::max<size_t>(g_eng.stream_min, 1));
-    const int K = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(g_eng.stream_slices, 8), n / per));
+    const size_t per = std::min<size_t>((size_t)1 << 17, std::max<size_t>(tn.stream_min, 1));
+    const int K = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(tn.stream_slices, 8), n / per));
     Plan pl;
     if (tbl) {  // resident fixed-base table: the table fixes the width, one bucket set
         pl.c = tbl->c;
         pl.nwin = tbl->nwin;
         pl.nbw = pl.nb = 1u << (pl.c - 1);
-    } else auto_plan(n, g2, g_eng.glv_mode, std::min(g_eng.window_override, 22), pl);
+    } else auto_plan(n, g2, tn.glv_mode, tn.window_override, pl);
     if (h_bases)
         if (int rc = cx.bases.reserve(n * AB)) return rc;
     if (cx.busy_valid) CUDA_TRY(cudaStreamWaitEvent(cx.stream, cx.ev_busy, 0));
@@ -528,11 +624,11 @@ int msm_streamed(int group, DeviceCtx &cx, const void *h_bases, const void *d_re
     // slice k while the host is stuck copying slice k+1 (19.5 → 13.7 ms at G1 2^20 one-shot).
     for (int k = 0; k < K; k++) {
         const size_t lo = n * k / K, hi = n * (k + 1) / K;
-        cudaMemcpyAsync((char *)cx.scalars.p + lo * 32, h_scalars + 4 * lo, (hi - lo) * 32, cudaMemcpyHostToDevice, cx.copy_stream);
-        cudaEventRecord(cx.ev_slice[2 * k], cx.copy_stream);
+        CUDA_TRY(cudaMemcpyAsync((char *)cx.scalars.p + lo * 32, h_scalars + 4 * lo, (hi - lo) * 32, cudaMemcpyHostToDevice, cx.copy_stream));
+        CUDA_TRY(cudaEventRecord(cx.ev_slice[2 * k], cx.copy_stream));
         if (h_bases) {
-            cudaMemcpyAsync((char *)cx.bases.p + lo * AB, (const char *)h_bases + lo * AB, (hi - lo) * AB, cudaMemcpyHostToDevice, cx.copy_stream);
-            cudaEventRecord(cx.ev_slice[2 * k + 1], cx.copy_stream);
+            CUDA_TRY(cudaMemcpyAsync((char *)cx.bases.p + lo * AB, (const char *)h_bases + lo * AB, (hi - lo) * AB, cudaMemcpyHostToDevice, cx.copy_stream));
+            CUDA_TRY(cudaEventRecord(cx.ev_slice[2 * k + 1], cx.copy_stream));
         }
         PassOpts po;
         po.plan = &pl;
@@ -541,13 +637,117 @@ int msm_streamed(int group, DeviceCtx &cx, const void *h_bases, const void *d_re
         TableRef sub;
         if (tbl) { sub = *tbl; sub.p = (const char *)tbl->p + lo * AB; }  // same stride, shifted origin
         CUDA_TRY(cudaStreamWaitEvent(cx.stream, cx.ev_slice[2 * k], 0));
-        if (int rc = run_pass(group, cx, dev_bases ? dev_bases + lo * AB : nullptr, (const char *)cx.scalars.p + lo * 32, hi - lo, mont, cx.out.p,
+        if (int rc = run_pass(group, cx, tn, dev_bases ? dev_bases + lo * AB : nullptr, (const char *)cx.scalars.p + lo * 32, hi - lo, mont, cx.out.p,
                               cx.stream, h_bases ? cx.ev_slice[2 * k + 1] : nullptr, tbl ? &sub : nullptr, po))
             return rc;
     }
     CUDA_TRY(cudaEventRecord(cx.ev_busy, cx.stream));
     cx.busy_valid = true;
     return 0;
+}
+
+// Wait for everything a context may still have in flight.  Error paths call this before
+// returning: the caller owns `bases` / `scalars` again the moment the call returns, so no copy
+// may still be reading them (with page-locked memory the H2D copies are truly asynchronous), and
+// the next call must not find work left over on the side streams.
+void drain(DeviceCtx &cx) {
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(cx.dev);
+    for (cudaStream_t st : {cx.copy_stream, cx.stream, cx.aux_stream, cx.tail_stream}) cudaStreamSynchronize(st);
+    cudaGetLastError();
+    cx.busy_valid = false;
+    cudaSetDevice(prev);
+}
+
+// One device's share of a host-buffer MSM: uploads (streamed in slices when large), the whole
+// pipeline, result in the first Jacobian slot of cx.out.  Asynchronous; ctx.mu held, ctx.dev current.
+struct Share {
+    int group = 0, mont = 0, d = 0;
+    const uint64_t *bases = nullptr, *scalars = nullptr;  // already offset to this device's range
+    size_t cnt = 0;
+    const b200msm_bases *resident = nullptr;
+    Tun tn;
+};
+int device_share(DeviceCtx &cx, const Share &sh) {
+    const size_t AB = aff_bytes(sh.group), JB = jac_bytes(sh.group);
+    const b200msm_bases *resident = sh.resident;
+    const int d = sh.d;
+    if (sh.cnt == 0) {
+        if (cx.busy_valid) CUDA_TRY(cudaStreamWaitEvent(cx.stream, cx.ev_busy, 0));
+        CUDA_TRY(cudaMemsetAsync(cx.out.p, 0, JB, cx.stream));
+        return 0;
+    }
+    if (int rc = cx.scalars.reserve(sh.cnt * 32)) return rc;
+    // large enough to be worth slicing (and, for resident bases, small enough for one pass per slice set)
+    if (sh.cnt >= sh.tn.stream_min && sh.tn.stream_slices > 1 && sh.cnt <= ((size_t)1 << 24) && !sh.tn.max_chunk_override) {
+        if (!resident) return msm_streamed(sh.group, cx, sh.tn, sh.bases, nullptr, nullptr, sh.scalars, sh.cnt, sh.mont);
+        if (resident->tbl_c) {
+            TableRef tr{resident->table[d].p, resident->cnt[d], resident->tbl_c, resident->tbl_nwin};
+            return msm_streamed(sh.group, cx, sh.tn, nullptr, nullptr, &tr, sh.scalars, sh.cnt, sh.mont);
+        }
+        return msm_streamed(sh.group, cx, sh.tn, nullptr, resident->shard[d].p, nullptr, sh.scalars, sh.cnt, sh.mont);
+    }
+    // the previous call's kernels may still read cx.scalars / cx.bases
+    if (cx.busy_valid) CUDA_TRY(cudaStreamWaitEvent(cx.copy_stream, cx.ev_busy, 0));
+    // scalars first (the digit kernel needs them), then the bases behind them on the same copy
+    // stream; the compute stream only waits for the bases right before the accumulation
+    CUDA_TRY(cudaMemcpyAsync(cx.scalars.p, sh.scalars, sh.cnt * 32, cudaMemcpyHostToDevice, cx.copy_stream));
+    CUDA_TRY(cudaEventRecord(cx.ev_scalars, cx.copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(cx.stream, cx.ev_scalars, 0));
+    const void *db;
+    cudaEvent_t ready = nullptr;
+    TableRef tr{nullptr, 0, 0, 0};
+    if (resident && resident->tbl_c) {
+        tr = TableRef{resident->table[d].p, resident->cnt[d], resident->tbl_c, resident->tbl_nwin};
+        db = tr.p;
+    } else if (resident) db = resident->shard[d].p;
+    else {
+        if (int rc = cx.bases.reserve(sh.cnt * AB)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(cx.bases.p, sh.bases, sh.cnt * AB, cudaMemcpyHostToDevice, cx.copy_stream));
+        CUDA_TRY(cudaEventRecord(cx.ev_bases, cx.copy_stream));
+        db = cx.bases.p;
+        ready = cx.ev_bases;
+    }
+    return run_group(sh.group, cx, sh.tn, db, cx.scalars.p, sh.cnt, sh.mont, cx.out.p, cx.stream, ready, tr.c ? &tr : nullptr);
+}
+
+// One persistent host thread per bound device (only when more than one is bound).  The calling
+// thread hands every device its share and sleeps; the workers issue copies and launches in
+// parallel (a streamed share is ≈ 300 launches and, from pageable memory, blocking staged
+// copies — issued device after device from one thread they would serialise), each sends its
+// partial to device 0 over NVLink, and the caller adds the partials there.
+void DeviceWorker::loop() {
+        cudaSetDevice(cx->dev);
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return quit || job; });
+            if (quit) return;
+            const Share *sh = job;
+            lk.unlock();
+            int r;
+            {
+                std::lock_guard<std::mutex> cl(cx->mu);
+                r = device_share(*cx, *sh);
+                const size_t JB = jac_bytes(sh->group);
+                if (!r && gather_dst) {  // partial → device 0 (peer copy over NVLink), then mark the share complete
+                    cudaError_t e = cudaMemcpyPeerAsync(gather_dst, gather_dev, cx->out.p, cx->dev, JB, cx->stream);
+                    if (e != cudaSuccess) r = fail(B200MSM_ECUDA, std::string("peer copy of a partial: ") + cudaGetErrorString(e));
+                }
+                if (!r) {
+                    cudaError_t e = cudaEventRecord(cx->ev_share, cx->stream);
+                    if (e != cudaSuccess) r = fail(B200MSM_ECUDA, std::string("cudaEventRecord: ") + cudaGetErrorString(e));
+                }
+                if (r) drain(*cx);
+            }
+            lk.lock();
+            rc = r;
+            err = r ? g_err : std::string();
+            job = nullptr;
+            done = true;
+            cv.notify_all();
+        }
+    
 }
 
 int msm_host(int group, const uint64_t *bases, const uint64_t *scalars, size_t n, int mont, uint64_t *out,
@@ -557,90 +757,95 @@ int msm_host(int group, const uint64_t *bases, const uint64_t *scalars, size_t n
     if (int rc = engine_init(-1, 1)) return rc;
     const size_t AB = aff_bytes(group), JB = jac_bytes(group);
     const int ndev = (int)g_eng.ctx.size();
+    if (resident) {
+        if (resident->generation != g_eng.generation || (int)resident->shard.size() != ndev)
+            return fail(B200MSM_EINVAL, "resident bases were uploaded under another engine binding (b200msm_shutdown / b200msm_init since)");
+    }
     if (n == 0) {
         memset(out, 0, JB);
         return 0;
     }
+    const Tun tn = tun_snapshot();
     int prev_dev = 0;
     cudaGetDevice(&prev_dev);
     // index ranges: the upload's own split when resident, else an even split
-    std::vector<size_t> lo(ndev), cnt(ndev);
+    std::vector<Share> shares(ndev);
     for (int d = 0; d < ndev; d++) {
+        size_t lo, cnt;
         if (resident) {
-            lo[d] = resident->lo[d];
-            cnt[d] = lo[d] >= n ? 0 : std::min(resident->cnt[d], n - lo[d]);
+            lo = resident->lo[d];
+            cnt = lo >= n ? 0 : std::min(resident->cnt[d], n - lo);
         } else {
-            lo[d] = n * d / ndev;
-            cnt[d] = n * (d + 1) / ndev - lo[d];
+            lo = n * d / ndev;
+            cnt = n * (d + 1) / ndev - lo;
         }
+        Share &sh = shares[d];
+        sh.group = group; sh.mont = mont; sh.d = d; sh.cnt = cnt; sh.resident = resident; sh.tn = tn;
+        sh.bases = bases ? (const uint64_t *)((const char *)bases + lo * AB) : nullptr;
+        sh.scalars = scalars + 4 * lo;
     }
-    std::vector<std::unique_lock<std::mutex>> locks;
-    for (auto &c : g_eng.ctx) locks.emplace_back(c->mu);
     int rc = 0;
-    // issue everything asynchronously on every device, then collect
-    for (int d = 0; d < ndev && !rc; d++) {
-        DeviceCtx &cx = *g_eng.ctx[d];
-        cudaSetDevice(cx.dev);
-        if ((rc = cx.out.reserve(JB * (size_t)(ndev + 1)))) break;
-        if (cnt[d] == 0) {
-            cudaMemsetAsync(cx.out.p, 0, JB, cx.stream);
-            continue;
-        }
-        if ((rc = cx.scalars.reserve(cnt[d] * 32))) break;
-        // large enough to be worth slicing (and, for resident bases, small enough for one pass per slice set)
-        if (cnt[d] >= g_eng.stream_min && g_eng.stream_slices > 1 && cnt[d] <= ((size_t)1 << 24) && !g_eng.max_chunk_override) {
-            if (!resident) rc = msm_streamed(group, cx, (const char *)bases + lo[d] * AB, nullptr, nullptr, scalars + 4 * lo[d], cnt[d], mont);
-            else if (resident->tbl_c) {
-                TableRef tr{resident->table[d].p, resident->cnt[d], resident->tbl_c, resident->tbl_nwin};
-                rc = msm_streamed(group, cx, nullptr, nullptr, &tr, scalars + 4 * lo[d], cnt[d], mont);
-            } else rc = msm_streamed(group, cx, nullptr, resident->shard[d].p, nullptr, scalars + 4 * lo[d], cnt[d], mont);
-            continue;
-        }
-        // scalars first (the digit kernel needs them), then the bases behind them on the same copy
-        // stream; the compute stream only waits for the bases right before the accumulation
-        cudaMemcpyAsync(cx.scalars.p, scalars + 4 * lo[d], cnt[d] * 32, cudaMemcpyHostToDevice, cx.copy_stream);
-        cudaEventRecord(cx.ev_scalars, cx.copy_stream);
-        cudaStreamWaitEvent(cx.stream, cx.ev_scalars, 0);
-        const void *db;
-        cudaEvent_t ready = nullptr;
-        TableRef tr{nullptr, 0, 0, 0};
-        if (resident && resident->tbl_c) {
-            tr = TableRef{resident->table[d].p, resident->cnt[d], resident->tbl_c, resident->tbl_nwin};
-            db = tr.p;
-        } else if (resident) db = resident->shard[d].p;
-        else {
-            if ((rc = cx.bases.reserve(cnt[d] * AB))) break;
-            cudaMemcpyAsync(cx.bases.p, (const char *)bases + lo[d] * AB, cnt[d] * AB, cudaMemcpyHostToDevice, cx.copy_stream);
-            cudaEventRecord(cx.ev_bases, cx.copy_stream);
-            db = cx.bases.p;
-            ready = cx.ev_bases;
-        }
-        rc = run_group(group, cx, db, cx.scalars.p, cnt[d], mont, cx.out.p, cx.stream, ready, tr.c ? &tr : nullptr);
-    }
-    if (!rc) {
-        DeviceCtx &c0 = *g_eng.ctx[0];
-        if (ndev == 1) {
-            cudaSetDevice(c0.dev);
-            cudaMemcpyAsync(out, c0.out.p, JB, cudaMemcpyDeviceToHost, c0.stream);
-            cudaError_t e = cudaStreamSynchronize(c0.stream);
+    DeviceCtx &c0 = *g_eng.ctx[0];
+    if (ndev == 1) {
+        std::lock_guard<std::mutex> lk(c0.mu);
+        cudaSetDevice(c0.dev);
+        if (!(rc = c0.out.reserve(JB * 2)) && !(rc = device_share(c0, shares[0]))) {
+            cudaError_t e = cudaMemcpyAsync(out, c0.out.p, JB, cudaMemcpyDeviceToHost, c0.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c0.stream);
             if (e != cudaSuccess) rc = fail(B200MSM_ECUDA, std::string("msm: ") + cudaGetErrorString(e));
-        } else {
-            // gather the per-device partials on device 0 (peer copies over NVLink), add, download
-            for (int d = 1; d < ndev && !rc; d++) {
-                DeviceCtx &cx = *g_eng.ctx[d];
-                cudaSetDevice(cx.dev);
-                cudaError_t e = cudaStreamSynchronize(cx.stream);
-                if (e != cudaSuccess) { rc = fail(B200MSM_ECUDA, std::string("msm shard: ") + cudaGetErrorString(e)); break; }
-                cudaMemcpyPeerAsync((char *)c0.out.p + JB * (size_t)d, c0.dev, cx.out.p, cx.dev, JB, c0.stream);
+        }
+        if (rc) drain(c0);
+    } else {
+        std::lock_guard<std::mutex> ml(g_eng.multi_mu);
+        // result slots: every device's own partial in its slot 0; device 0 also holds the gathered partials 1..ndev−1 and the sum
+        for (int d = 0; d < ndev && !rc; d++) {
+            DeviceCtx &cx = *g_eng.ctx[d];
+            std::lock_guard<std::mutex> lk(cx.mu);
+            cudaSetDevice(cx.dev);
+            rc = cx.out.reserve(JB * (size_t)(ndev + 1));
+        }
+        if (!rc) {
+            for (int d = 0; d < ndev; d++) {
+                DeviceWorker &w = *g_eng.workers[d];
+                std::lock_guard<std::mutex> lk(w.mu);
+                w.gather_dst = d ? (char *)c0.out.p + JB * (size_t)d : nullptr;
+                w.gather_dev = c0.dev;
+                w.done = false;
+                w.job = &shares[d];
+                w.cv.notify_all();
             }
+            for (int d = 0; d < ndev; d++) {       // every share issued (not yet finished)
+                DeviceWorker &w = *g_eng.workers[d];
+                std::unique_lock<std::mutex> lk(w.mu);
+                w.cv.wait(lk, [&] { return w.done; });
+                if (w.rc && !rc) rc = fail(w.rc, w.err);
+            }
+            std::lock_guard<std::mutex> lk(c0.mu);
+            cudaSetDevice(c0.dev);
             if (!rc) {
-                cudaSetDevice(c0.dev);
+                // device 0 waits for every share (its own included), adds the partials, downloads
+                cudaError_t e = cudaSuccess;
+                for (int d = 1; d < ndev && e == cudaSuccess; d++) e = cudaStreamWaitEvent(c0.stream, g_eng.ctx[d]->ev_share, 0);
                 void *sum = (char *)c0.out.p + JB * (size_t)ndev;
-                (group == B200MSM_G1 ? launch_sum_partials_g1 : launch_sum_partials_g2)((const uint32_t *)c0.out.p, ndev, (uint32_t *)sum, c0.stream);
-                cudaMemcpyAsync(out, sum, JB, cudaMemcpyDeviceToHost, c0.stream);
-                cudaError_t e = cudaStreamSynchronize(c0.stream);
+                if (e == cudaSuccess) {
+                    (group == B200MSM_G1 ? launch_sum_partials_g1 : launch_sum_partials_g2)((const uint32_t *)c0.out.p, ndev, (uint32_t *)sum, c0.stream);
+                    e = cudaMemcpyAsync(out, sum, JB, cudaMemcpyDeviceToHost, c0.stream);
+                }
+                if (e == cudaSuccess) e = cudaStreamSynchronize(c0.stream);
                 if (e != cudaSuccess) rc = fail(B200MSM_ECUDA, std::string("msm combine: ") + cudaGetErrorString(e));
+                // the other devices are idle now (device 0 waited for them), but say so to their contexts:
+                // the caller's buffers must not be in use once we return
+                for (int d = 1; d < ndev; d++) {
+                    cudaSetDevice(g_eng.ctx[d]->dev);
+                    cudaError_t e2 = cudaStreamSynchronize(g_eng.ctx[d]->stream);
+                    if (e2 != cudaSuccess && !rc) rc = fail(B200MSM_ECUDA, std::string("msm shard: ") + cudaGetErrorString(e2));
+                }
             }
+        }
+        if (rc) {
+            const std::string keep = g_err;
+            for (int d = 0; d < ndev; d++) drain(*g_eng.ctx[d]);
+            g_err = keep;
         }
     }
     cudaSetDevice(prev_dev);
@@ -655,9 +860,19 @@ extern "C" {
 int b200msm_init(int first_device, int n_devices) { return engine_init(first_device, n_devices); }
 
 void b200msm_shutdown(void) {
+    std::lock_guard<std::mutex> ml(g_eng.multi_mu);
     std::lock_guard<std::mutex> lk(g_eng.mu);
     int prev = 0;
     cudaGetDevice(&prev);
+    for (auto &w : g_eng.workers) {
+        {
+            std::lock_guard<std::mutex> wl(w->mu);
+            w->quit = true;
+            w->cv.notify_all();
+        }
+        w->th.join();
+    }
+    g_eng.workers.clear();
     for (auto &c : g_eng.ctx) destroy_ctx(*c);
     for (auto &c : g_eng.lane_ctx) destroy_ctx(*c);
     g_eng.lane_ctx.clear();
@@ -665,7 +880,10 @@ void b200msm_shutdown(void) {
     g_eng.inited = false;
     cudaSetDevice(prev);
 }
-int b200msm_device_count(void) { return (int)g_eng.ctx.size(); }
+int b200msm_device_count(void) {
+    std::lock_guard<std::mutex> lk(g_eng.mu);
+    return (int)g_eng.ctx.size();
+}
 const char *b200msm_last_error(void) { return g_err.c_str(); }
 const char *b200msm_version(void) { return "b200msm 0.1 (sm_100a)"; }
 
@@ -685,6 +903,8 @@ int b200msm_bases_upload(int group, const uint64_t *bases, size_t n, b200msm_bas
     h->n = n;
     const int ndev = (int)g_eng.ctx.size();
     const size_t AB = aff_bytes(group);
+    h->generation = g_eng.generation;
+    for (auto &c : g_eng.ctx) h->dev.push_back(c->dev);
     h->shard.resize(ndev);
     h->lo.resize(ndev);
     h->cnt.resize(ndev);
@@ -712,10 +932,13 @@ int b200msm_bases_free(b200msm_bases *h) {
     if (!h) return 0;
     int prev = 0;
     cudaGetDevice(&prev);
-    for (size_t d = 0; d < h->shard.size() && d < g_eng.ctx.size(); d++) {
-        cudaSetDevice(g_eng.ctx[d]->dev);
-        h->shard[d].release();
-        if (d < h->table.size()) h->table[d].release();
+    {
+        std::lock_guard<std::mutex> hl(h->mu);   // a b200msm_run still using the handle finishes first
+        for (size_t d = 0; d < h->shard.size(); d++) {   // by the device ids of the upload: valid after b200msm_shutdown too
+            cudaSetDevice(h->dev[d]);
+            h->shard[d].release();
+            if (d < h->table.size()) h->table[d].release();
+        }
     }
     cudaSetDevice(prev);
     delete h;
@@ -724,6 +947,7 @@ int b200msm_bases_free(b200msm_bases *h) {
 int b200msm_run(const b200msm_bases *h, const uint64_t *scalars, size_t n, int mont, uint64_t *out) {
     if (!h) return fail(B200MSM_EINVAL, "null handle");
     if (n > h->n) return fail(B200MSM_EINVAL, "n exceeds the uploaded base count");
+    std::lock_guard<std::mutex> hl(h->mu);       // not while b200msm_bases_precompute swaps the shards for tables
     return msm_host(h->group, nullptr, scalars, n, mont, out, h);
 }
 
@@ -741,9 +965,12 @@ int b200msm_table_plan(int group, size_t n, int *window_bits, int *windows) {
 }
 int b200msm_bases_precompute(b200msm_bases *h, int window_bits) {
     if (!h) return fail(B200MSM_EINVAL, "null handle");
+    std::lock_guard<std::mutex> hl(h->mu);
     if (h->tbl_c) return 0;  // already a table
     if (int rc = engine_init(-1, 1)) return rc;
-    const int ndev = (int)std::min(g_eng.ctx.size(), h->shard.size());
+    if (h->generation != g_eng.generation || h->shard.size() != g_eng.ctx.size())
+        return fail(B200MSM_EINVAL, "resident bases were uploaded under another engine binding (b200msm_shutdown / b200msm_init since)");
+    const int ndev = (int)h->shard.size();
     size_t maxcnt = 0;
     for (int d = 0; d < ndev; d++) maxcnt = std::max(maxcnt, h->cnt[d]);
     int c = window_bits, nwin = 0;
@@ -814,7 +1041,7 @@ int b200msm_run_table_device(int group, const void *d_table, size_t stride, int 
     if (!cx) return fail(B200MSM_EINVAL, "current device is not bound to the engine");
     std::lock_guard<std::mutex> lk(cx->mu);
     TableRef tr{d_table, stride, window_bits, (256 + window_bits - 1) / window_bits};
-    return run_group(group, *cx, d_table, d_scalars, n, mont, d_out, (cudaStream_t)stream, nullptr, &tr);
+    return run_group(group, *cx, tun_snapshot(), d_table, d_scalars, n, mont, d_out, (cudaStream_t)stream, nullptr, &tr);
 }
 
 int b200msm_run_device(int group, const void *d_bases, const void *d_scalars, size_t n, int mont, void *d_out,
@@ -824,7 +1051,7 @@ int b200msm_run_device(int group, const void *d_bases, const void *d_scalars, si
     DeviceCtx *cx = ctx_for_current_device();
     if (!cx) return fail(B200MSM_EINVAL, "current device is not bound to the engine");
     std::lock_guard<std::mutex> lk(cx->mu);
-    return run_group(group, *cx, d_bases, d_scalars, n, mont, d_out, (cudaStream_t)stream);
+    return run_group(group, *cx, tun_snapshot(), d_bases, d_scalars, n, mont, d_out, (cudaStream_t)stream);
 }
 int b200msm_sum_partials_device(int group, const void *d_partials, int count, void *d_out, void *stream) {
     if (!d_partials || !d_out || count < 0) return fail(B200MSM_EINVAL, "bad argument");
@@ -920,14 +1147,16 @@ int b200msm_serialize(int group, const uint64_t *affine, size_t n, int compresse
 }
 
 int b200msm_set_window_bits(int c) {
-    if (c < 0 || c == 1 || c > 24) return fail(B200MSM_EINVAL, "window bits must be 0 (auto) or 2..24");
-    g_eng.window_override = c;
+    if (c < 0 || c == 1 || c > 22) return fail(B200MSM_EINVAL, "window bits must be 0 (auto) or 2..22");
+    tun_update([&](Tun &t) { t.window_override = c; });
     return 0;
 }
 int b200msm_set_stream_slices(int slices, size_t min_points) {
     if (slices < 1 || slices > 8) return fail(B200MSM_EINVAL, "stream slices must be 1 (off) .. 8");
-    g_eng.stream_slices = slices;
-    g_eng.stream_min = min_points ? min_points : (size_t)1 << 18;
+    tun_update([&](Tun &t) {
+        t.stream_slices = slices;
+        t.stream_min = min_points ? min_points : (size_t)1 << 18;
+    });
     return 0;
 }
 int b200msm_host_register(const void *ptr, size_t bytes) {
@@ -947,20 +1176,20 @@ int b200msm_set_lane(int lane) {
 }
 int b200msm_set_heavy_factor(int f) {
     if (f < 0 || f > 1 << 20) return fail(B200MSM_EINVAL, "heavy factor must be 0 (automatic) or 1..2^20");
-    g_eng.heavy_factor = f;
+    tun_update([&](Tun &t) { t.heavy_factor = f; });
     return 0;
 }
 int b200msm_set_glv(int mode) {
     if (mode < -1 || mode > 1) return fail(B200MSM_EINVAL, "glv mode must be -1 (auto), 0 (off) or 1 (on)");
-    g_eng.glv_mode = mode;
+    tun_update([&](Tun &t) { t.glv_mode = mode; });
     return 0;
 }
 int b200msm_set_max_chunk(size_t max_points_per_pass) {
-    g_eng.max_chunk_override = max_points_per_pass;
+    tun_update([&](Tun &t) { t.max_chunk_override = max_points_per_pass; });
     return 0;
 }
 int b200msm_set_profiling(int on) {
-    g_eng.profiling = on != 0;
+    tun_update([&](Tun &t) { t.profiling = on != 0; }, false);
     return 0;
 }
 int b200msm_plan_query(int group, size_t n, int glv_mode, int out[4]) {

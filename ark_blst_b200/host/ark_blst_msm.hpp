@@ -45,6 +45,15 @@ template <class T> struct Result {
     static Result Err(usize e) { return Result{false, T{}, e}; }
 };
 
+// Engine binding — the counterpart of the reference's `Device::all()` + `devices[0]`
+// (src/gpu.rs:233-234): which GPUs a sharded MSM runs on.  Mirrors rust/gpu.rs
+// init_devices / shutdown_devices / device_count.  Optional: without it the first msm binds the
+// current device only.  Binding another range while bound is Err(0) (shutdown_devices first).
+inline Result<usize> init_devices(usize first_device, usize n_devices /* 0 = all visible */);
+inline void shutdown_devices() { b200msm_shutdown(); }
+inline usize device_count() { return static_cast<usize>(b200msm_device_count()); }
+inline std::string last_error() { return b200msm_last_error(); }
+
 namespace detail {
 template <class Proj, class Aff>
 Result<Proj> call(int (*f)(const uint64_t *, const uint64_t *, size_t, int, uint64_t *), const Aff *bases, usize nb,
@@ -56,6 +65,11 @@ Result<Proj> call(int (*f)(const uint64_t *, const uint64_t *, size_t, int, uint
     return Result<Proj>::Ok(out);
 }
 }  // namespace detail
+
+inline Result<usize> init_devices(usize first_device, usize n_devices) {
+    if (b200msm_init(static_cast<int>(first_device), static_cast<int>(n_devices)) != 0) return Result<usize>::Err(0);
+    return Result<usize>::Ok(device_count());
+}
 
 struct G1Projective {                    // blst_p1 (Jacobian)
     uint64_t l[18];

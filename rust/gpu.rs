@@ -5,30 +5,62 @@
 //! them on the host (src/gpu.rs:126-241).  This file shrinks to an `extern "C"` block over
 //! `libb200msm.so` (include/b200msm.h); planning, kernels and the whole reduction live there.
 //!
+//! Install: copy this file over `src/gpu.rs`, `rust/build.rs` over `build.rs`, then
+//! `patch -p1 < rust/ark-blst-b200.patch` (Cargo.toml, src/lib.rs, src/g1.rs, src/g2.rs; applies
+//! cleanly to the reference tree — tests/test_rust_patch.py dry-runs it).
+//!
 //! NOT COMPILED IN THIS REPOSITORY: the build image has no cargo/rustc.  The struct sizes the
 //! pointer casts rely on are asserted at compile time below and mirrored by C `_Static_assert`s in
 //! tests/test_layout_mirror.c.
 #![cfg(feature = "b200")]
 
-use ark_ec::AffineRepr;
+use core::ffi::{c_char, c_int, c_void};
+use core::marker::PhantomData;
 
 use crate::{g1::G1Affine, g1::G1Projective, g2::G2Affine, g2::G2Projective, scalar::Scalar};
 
-#[allow(non_camel_case_types)]
-type c_int = core::ffi::c_int;
-
 #[link(name = "b200msm")]
 extern "C" {
+    // engine binding: which GPUs a sharded MSM runs on (reference: Device::all()[0], src/gpu.rs:233-234)
+    fn b200msm_init(first_device: c_int, n_devices: c_int) -> c_int;
+    fn b200msm_shutdown();
+    fn b200msm_device_count() -> c_int;
+    fn b200msm_last_error() -> *const c_char;
     fn b200msm_g1(bases: *const u64, scalars: *const u64, n: usize, scalars_are_montgomery: c_int, out: *mut u64) -> c_int;
     fn b200msm_g2(bases: *const u64, scalars: *const u64, n: usize, scalars_are_montgomery: c_int, out: *mut u64) -> c_int;
     // resident bases (a proving key uploaded once) and their fixed-base window table
-    fn b200msm_bases_upload(group: c_int, bases: *const u64, n: usize, handle: *mut *mut core::ffi::c_void) -> c_int;
-    fn b200msm_bases_precompute(handle: *mut core::ffi::c_void, window_bits: c_int) -> c_int;
-    fn b200msm_run(handle: *const core::ffi::c_void, scalars: *const u64, n: usize, scalars_are_montgomery: c_int, out: *mut u64) -> c_int;
-    fn b200msm_bases_free(handle: *mut core::ffi::c_void) -> c_int;
+    fn b200msm_bases_upload(group: c_int, bases: *const u64, n: usize, handle: *mut *mut c_void) -> c_int;
+    fn b200msm_bases_precompute(handle: *mut c_void, window_bits: c_int) -> c_int;
+    fn b200msm_run(handle: *const c_void, scalars: *const u64, n: usize, scalars_are_montgomery: c_int, out: *mut u64) -> c_int;
+    fn b200msm_bases_free(handle: *mut c_void) -> c_int;
     // page-lock a long-lived host buffer (a Vec is pageable memory: the driver stages it at a fraction of the PCIe rate)
-    fn b200msm_host_register(ptr: *const core::ffi::c_void, bytes: usize) -> c_int;
-    fn b200msm_host_unregister(ptr: *const core::ffi::c_void) -> c_int;
+    fn b200msm_host_register(ptr: *const c_void, bytes: usize) -> c_int;
+    fn b200msm_host_unregister(ptr: *const c_void) -> c_int;
+}
+
+/// Bind the engine to `n_devices` GPUs starting at `first_device` (`n_devices = 0`: all visible).
+/// Every later `msm` shards its points evenly over them and adds the per-GPU partials on the
+/// first one.  Optional: without it the first `msm` binds the current device only.  Binding a
+/// different range while bound is an error (`shutdown_devices` first).
+pub fn init_devices(first_device: usize, n_devices: usize) -> Result<usize, usize> {
+    let rc = unsafe { b200msm_init(first_device as c_int, n_devices as c_int) };
+    if rc != 0 { Err(0) } else { Ok(device_count()) }
+}
+/// Release every device buffer, stream and worker thread of the engine.  Resident bases uploaded
+/// before must be dropped or re-uploaded: they do not survive a re-binding.
+pub fn shutdown_devices() {
+    unsafe { b200msm_shutdown() }
+}
+pub fn device_count() -> usize {
+    unsafe { b200msm_device_count() as usize }
+}
+/// The library's message for the calling thread's most recent failure.
+pub fn last_error() -> String {
+    let p = unsafe { b200msm_last_error() };
+    if p.is_null() {
+        return String::new();
+    }
+    unsafe { std::ffi::CStr::from_ptr(p) }.to_string_lossy().into_owned()
 }
 
 /// Page-locks `buf` for as long as the guard lives, so `msm` copies from it at full PCIe rate.
@@ -110,40 +142,67 @@ pub(crate) fn msm_g2(bases: &[G2Affine], scalars: Scalars<'_>) -> Result<G2Proje
     Ok(unsafe { out.assume_init() })
 }
 
-// keep the generic bound the old entry point had so call sites outside g1.rs/g2.rs still name it
-#[allow(dead_code)]
-pub(crate) fn _assert_affine<G: AffineRepr>() {}
-
-/// A proving key's G1 bases kept on the device(s): `upload` once, `msm` per proof (32 B/point of
-/// H2D instead of 128). `precompute` turns them into a fixed-base window table (no Horner chain,
-/// one-window bucket reduction). The reference has no counterpart: it re-uploads the bases and
-/// rebuilds its program on every call (src/gpu.rs:149-150,233-237).
-pub struct ResidentG1Bases {
-    handle: *mut core::ffi::c_void,
-    len: usize,
+/// The two groups the engine knows, as the C-ABI numbers them (B200MSM_G1 / B200MSM_G2).
+pub trait MsmGroup {
+    type Affine;
+    type Projective;
+    const ID: c_int;
 }
-unsafe impl Send for ResidentG1Bases {}
-unsafe impl Sync for ResidentG1Bases {}
+pub struct G1Tag;
+pub struct G2Tag;
+impl MsmGroup for G1Tag {
+    type Affine = G1Affine;
+    type Projective = G1Projective;
+    const ID: c_int = 0;
+}
+impl MsmGroup for G2Tag {
+    type Affine = G2Affine;
+    type Projective = G2Projective;
+    const ID: c_int = 1;
+}
 
-impl ResidentG1Bases {
-    pub fn upload(bases: &[G1Affine]) -> Result<Self, usize> {
+/// A proving key's bases kept on the device(s): `upload` once (sharded evenly over the bound
+/// GPUs), `msm` per proof (32 B/point of H2D instead of 128 / 224). `precompute` turns them into a
+/// fixed-base window table (no Horner chain, one-window bucket reduction). The reference has no
+/// counterpart: it re-uploads the bases and rebuilds its program on every call
+/// (src/gpu.rs:149-150,233-237).
+pub struct ResidentBases<G: MsmGroup> {
+    handle: *mut c_void,
+    len: usize,
+    _g: PhantomData<G>,
+}
+pub type ResidentG1Bases = ResidentBases<G1Tag>;
+pub type ResidentG2Bases = ResidentBases<G2Tag>;
+unsafe impl<G: MsmGroup> Send for ResidentBases<G> {}
+unsafe impl<G: MsmGroup> Sync for ResidentBases<G> {}
+
+impl<G: MsmGroup> ResidentBases<G> {
+    pub fn upload(bases: &[G::Affine]) -> Result<Self, usize> {
         let mut handle = core::ptr::null_mut();
-        let rc = unsafe { b200msm_bases_upload(0, bases.as_ptr() as *const u64, bases.len(), &mut handle) };
-        if rc != 0 { Err(0) } else { Ok(Self { handle, len: bases.len() }) }
+        let rc = unsafe { b200msm_bases_upload(G::ID, bases.as_ptr() as *const u64, bases.len(), &mut handle) };
+        if rc != 0 { Err(0) } else { Ok(Self { handle, len: bases.len(), _g: PhantomData }) }
+    }
+    pub fn len(&self) -> usize {
+        self.len
+    }
+    pub fn is_empty(&self) -> bool {
+        self.len == 0
     }
     pub fn precompute(&mut self) -> Result<(), usize> {
         if unsafe { b200msm_bases_precompute(self.handle, 0) } != 0 { Err(0) } else { Ok(()) }
     }
-    pub fn msm(&self, scalars: &[Scalar]) -> Result<G1Projective, usize> {
+    /// Σ sᵢ·Pᵢ over the first `scalars.len()` resident bases. `Err(len)` when more scalars than
+    /// bases are passed, `Err(0)` on a device error.
+    pub fn msm(&self, scalars: &[Scalar]) -> Result<G::Projective, usize> {
         if scalars.len() > self.len {
             return Err(self.len);
         }
-        let mut out = core::mem::MaybeUninit::<G1Projective>::uninit();
+        let mut out = core::mem::MaybeUninit::<G::Projective>::uninit();
         let rc = unsafe { b200msm_run(self.handle, scalars.as_ptr() as *const u64, scalars.len(), 1, out.as_mut_ptr() as *mut u64) };
         if rc != 0 { Err(0) } else { Ok(unsafe { out.assume_init() }) }
     }
 }
-impl Drop for ResidentG1Bases {
+impl<G: MsmGroup> Drop for ResidentBases<G> {
     fn drop(&mut self) {
         unsafe { b200msm_bases_free(self.handle) };
     }

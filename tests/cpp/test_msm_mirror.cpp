@@ -36,6 +36,12 @@ int main(int argc, char **argv) {
     for (int i = 0; i < 12; i++) std::sscanf(argv[1] + 16 * i, "%16lx", &g1[i]);
     for (int i = 0; i < 24; i++) std::sscanf(argv[2] + 16 * i, "%16lx", &g2[i]);
 
+    {   // bind every visible GPU (the reference takes devices[0], src/gpu.rs:233-234): a sharded MSM when there are several
+        auto nd = init_devices(0, 0);
+        CHECK(nd.is_ok() && nd.unwrap() >= 1 && device_count() == nd.unwrap());
+        CHECK(init_devices(0, 0).is_ok());                   // same binding again is fine
+        std::printf("devices bound: %zu\n", device_count());
+    }
     {   // G1: group_test MSM part
         const size_t n = 10;
         std::vector<G1Affine> bases(n + 3);

@@ -59,3 +59,45 @@ def test_concurrent_resident_and_oneshot(eng, cref):
     [t.join(180) for t in ths]
     rb.close()
     assert not errors, errors
+
+
+def test_setters_flipped_under_load(eng, cref):
+    """A thread flips the plan knobs (GLV mode, window width, slicing) while others run MSMs: every call
+    plans from ONE snapshot of the tunables, so results stay bit-exact whatever it catches."""
+    L = eng._lib.lib
+    n = 6000
+    bases = cref.synth_bases(0, 911, n)
+    sc = cref.synth_scalars(912, n, True)
+    exp = cref.msm(0, bases, sc, 1)
+    rb = eng.ResidentBases(eng.G1Projective, bases)
+    stop = threading.Event()
+    errors = []
+
+    def flip():
+        k = 0
+        while not stop.is_set():
+            L.b200msm_set_glv((-1, 0, 1)[k % 3])
+            L.b200msm_set_window_bits((0, 9, 12, 0, 14)[k % 5])
+            L.b200msm_set_stream_slices(1 + k % 8, 1024)
+            L.b200msm_set_heavy_factor((0, 2, 5)[k % 3])
+            k += 1
+
+    def work(resident):
+        try:
+            for _ in range(12):
+                got = rb.msm(sc) if resident else eng.G1Projective.msm(bases, sc)
+                if not cref.affine_equal(0, got, exp):
+                    errors.append("mismatch")
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    fl = threading.Thread(target=flip)
+    ws = [threading.Thread(target=work, args=(k % 2 == 0,)) for k in range(4)]
+    fl.start()
+    [t.start() for t in ws]
+    [t.join(300) for t in ws]
+    stop.set()
+    fl.join(10)
+    L.b200msm_set_glv(-1); L.b200msm_set_window_bits(0); L.b200msm_set_stream_slices(8, 0); L.b200msm_set_heavy_factor(0)
+    rb.close()
+    assert not errors, errors
