@@ -6,13 +6,24 @@ Contract (one JSON line from rank 0):
   python bench.py --impl reference --gpus N --steps K --warmup W  the reference's CPU path, timed
                                                                   on the box's host cores
 A "step" is one whole MSM (hot path: digits → sort → accumulate → reduce → combine) over one
-batch of synthetic input.  Workload at N=1: BASELINE.json configs[1], "G1 MSM 2^20 points on
-1×B200".  At N>1 every rank holds its own 2^20-point shard (weak scaling: an N·2^20-point MSM),
+batch of synthetic input.  Headline workload at N=1: BASELINE.json configs[1], "G1 MSM 2^20 points
+on 1×B200".  At N>1 every rank holds its own 2^20-point shard (weak scaling: an N·2^20-point MSM),
 computes a partial sum, the 144-byte partials are all-gathered over NCCL and rank 0 adds them.
 
 `value` / `ms_per_step`: device time per MSM with bases and scalars already resident in HBM.
 `e2e`: the same MSM through the reference-facing call b200msm_g1(host bases, host scalars) —
-H2D of 128 B/point and D2H of the result inside the timed region.
+H2D of 128 B/point and D2H of the result inside the timed region (pinned host memory;
+`e2e_pageable` is the same from ordinary pageable memory, what a Rust Vec is).
+
+Beside the headline the same line carries one block per remaining BASELINE.json config, each with
+its own parity check (`--blocks` selects; default all):
+  c0_2p16      configs[0]  G1 2^16, the benches/group.rs shape: GPU ms, and the CPU port's ms at N=1
+  strong_2p24  configs[2]  G1 2^24 sharded over the N ranks (strong scaling: total work fixed)
+  g2_2p20      configs[3]  G2 2^20 sharded over the N ranks
+  groth16_2p22 configs[4]  3×G1 + 1×G2 at 2^22, every MSM sharded over the N ranks, uniform and
+                           witness-like scalars
+  single_process (N>1)     the path a Rust caller takes: ONE process, b200msm_init(0, N),
+                           b200msm_g1(host, host) sharding G1 2^24 over the N GPUs inside the library
 """
 import argparse
 import json
@@ -30,6 +41,7 @@ METRIC = "BLS12-381 G1 MSM ms @2^20/2^24, 1-8 B200, vs blst Pippenger on host"
 SEED_BASES = 0xB200_0381_0000_0000
 SEED_SCALARS = 0xB200_0381_5CA1_A400
 FPMUL_IMAD = 588  # 32-bit IMAD per Fp product
+ALL_BLOCKS = ("c0_2p16", "g2_2p20", "strong_2p24", "groth16_2p22", "single_process")
 
 
 def work_model(n, g2, c=None):
@@ -44,6 +56,40 @@ def work_model(n, g2, c=None):
         if best is None or tot < best[2]:
             best = (cc, W, tot, acc)
     return best
+
+
+def work_model_counted(nonzero_digits, n, g2):
+    """The same model with the accumulate term COUNTED instead of assumed uniform: `nonzero_digits`
+    is the number of non-zero Booth digits of the actual scalars at the canonical c*(n) — the
+    bucket additions an MSM of these scalars has to perform (witness-like scalars are mostly 0/1)."""
+    madd, add, dbl = (28, 40, 25) if g2 else (10, 14, 9)
+    c, W, _, _ = work_model(n, g2)
+    return nonzero_digits * madd + W * 2 ** (c - 1) * 2 * add + W * (c * dbl + add)
+
+
+def count_nonzero_booth_digits(canon, c):
+    """canon: (n, 4) uint64 canonical scalars. Number of non-zero signed c-bit window digits
+    d_w = u_w + b[wc−1] − 2^c·b[wc+c−1] over W = ⌈256/c⌉ windows (numpy, exact)."""
+    import numpy as np
+
+    n = canon.shape[0]
+    W = math.ceil(256 / c)
+    limbs = np.concatenate([canon, np.zeros((n, 2), dtype=np.uint64)], axis=1)
+    total = 0
+    for w in range(W):
+        lo = w * c - 1                       # bits [lo, lo + c] → c+1 bits (bit −1 of window 0 is 0)
+        if lo < 0:
+            v = (limbs[:, 0] << np.uint64(1)) & np.uint64((1 << (c + 1)) - 1)
+        else:
+            q, r = divmod(lo, 64)
+            v = limbs[:, q] >> np.uint64(r)
+            if r + c + 1 > 64:
+                v = v | (limbs[:, q + 1] << np.uint64(64 - r))
+            v = v & np.uint64((1 << (c + 1)) - 1)
+        u = (v >> np.uint64(1)) & np.uint64((1 << c) - 1)
+        d = u.astype(np.int64) + (v & np.uint64(1)).astype(np.int64) - (((v >> np.uint64(c)) & np.uint64(1)).astype(np.int64) << c)
+        total += int(np.count_nonzero(d))
+    return total
 
 
 class ClockSampler:
@@ -106,12 +152,24 @@ def dist_env():
     return rank, world, local
 
 
+CPU_WHAT = ("oracle/libmsm_ref.so: C restatement of blst 0.3.10 Pippenger (window rule, Booth digits, XYZZ buckets, blst's "
+            "(slices x windows) tile grid on pthreads); Montgomery product = {mul}; real blst cannot be built here (Rust, "
+            "un-vendored, no cargo)")
+
+
+def cpu_what(cref):
+    adx = bool(cref.lib().ref_mul_impl())
+    return CPU_WHAT.format(mul="MULX/ADCX/ADOX inline asm (blst's mulx_mont_384 instruction mix)" if adx
+                           else "portable u128 (this CPU lacks ADX/BMI2)")
+
+
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
     """The reference's own CPU path for this MSM (src/g1.rs:602-619 → blstrs multi_exp → blst
     Pippenger), timed on the host cores. blst cannot be built here (Rust, un-vendored, no cargo),
-    so this times oracle/libmsm_ref.so — the C restatement of that algorithm — with every host
-    thread: cpu_baseline.kind = "port"."""
+    so this times oracle/libmsm_ref.so — the C restatement of that algorithm, with an ADX/MULX
+    Montgomery product where the CPU has it — with every host thread: cpu_baseline.kind = "port".
+    The FULL workload of our arm's config is timed at every N (N·2^20 points, no extrapolation)."""
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
@@ -120,36 +178,49 @@ def run_reference(args):
 
     g2 = args.group == "g2"
     n_total = (1 << args.logn) * args.gpus
-    n_s = min(n_total, 1 << args.ref_sample_logn)
     cores = cref.ncores()
     t0 = time.time()
-    bases = cref.synth_bases(int(g2), SEED_BASES, n_s)
-    scal = cref.synth_scalars(SEED_SCALARS, n_s, True)
+    bases = cref.synth_bases(int(g2), SEED_BASES, n_total)
+    scal = cref.synth_scalars(SEED_SCALARS, n_total, True)
     gen_s = time.time() - t0
     times = []
     out = None
-    for it in range(args.warmup + args.steps):
+    steps, warmup = args.steps, args.warmup
+    budget_s = 200.0      # the whole arm ends within a few minutes: fewer timed steps when one is long (reported)
+    t_arm = time.perf_counter()
+    it = 0
+    while it < warmup + steps:
         t0 = time.perf_counter()
         out = cref.msm(int(g2), bases, scal, 1, nthreads=cores)
         dt = (time.perf_counter() - t0) * 1e3
-        if it >= args.warmup:
+        if it >= warmup:
             times.append(dt)
-    ok = cref.affine_equal(int(g2), out, cref.msm_by_dlog(int(g2), SEED_BASES, cref.synth_scalars(SEED_SCALARS, n_s, False)))
-    ms_sample = sum(times) / len(times)
-    scale = n_total / n_s
-    ms = ms_sample * scale
-    sample = ("full workload" if n_s == n_total else
-              f"2^{args.ref_sample_logn} of {n_total} points per step, time scaled linearly x{scale:g}")
+        it += 1
+        if it == 1 and dt * 1e-3 * (warmup + steps) > budget_s:
+            warmup = 1
+            steps = max(2, min(steps, int(budget_s / (dt * 1e-3)) - 1))
+    ok = cref.affine_equal(int(g2), out, cref.msm_by_dlog(int(g2), SEED_BASES, cref.synth_scalars(SEED_SCALARS, n_total, False)))
+    ms = sum(times) / len(times)
+    # configs[0] on the CPU beside it (cheap): G1 2^16, the benches/group.rs:18-26 shape
+    n16 = 1 << 16
+    b16 = cref.synth_bases(0, SEED_BASES + 16, n16)
+    s16 = cref.synth_scalars(SEED_SCALARS + 16, n16, True)
+    t16 = []
+    for _ in range(4):
+        t0 = time.perf_counter()
+        cref.msm(0, b16, s16, 1, nthreads=cores)
+        t16.append((time.perf_counter() - t0) * 1e3)
     line = {
         "impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False,
+        "steps": len(times), "warmup": warmup, "ms_per_step": ms, "higher_is_better": False,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "points_per_s": n_total / (ms * 1e-3),
         "config": {"workload": f"{args.group.upper()} MSM 2^{args.logn} points per GPU x {args.gpus} GPU(s) = {n_total} points",
-                   "window_rule": "blst pippenger_window_size", "input_gen_s": round(gen_s, 2), "parity_vs_dlog": bool(ok)},
-        "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port", "sample": sample,
-                         "what": "oracle/libmsm_ref.so: C restatement of blst 0.3.10 Pippenger (portable u128 Montgomery, "
-                                 "no hand-written asm), pthreads over (window x slice) tiles"},
+                   "window_rule": "blst pippenger_window_size + breakdown", "input_gen_s": round(gen_s, 2), "parity_vs_dlog": bool(ok),
+                   "steps_requested": args.steps, "arm_wall_s": round(time.perf_counter() - t_arm, 1)},
+        "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port",
+                         "sample": f"the full workload: all {n_total} points per step, {len(times)} timed steps", "what": cpu_what(cref)},
+        "c0_2p16": {"workload": "G1 MSM 2^16 (benches/group.rs:18-26 shape) on the host cores", "cpu_ms": min(t16[1:]), "cores": cores},
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -158,267 +229,573 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+class Ctx:
+    """per-process state of our arm: device, stream, ranks, engine"""
+
+    def __init__(self, args):
+        import torch
+
+        import ark_blst_b200 as eng
+
+        self.torch, self.eng = torch, eng
+        self.rank, self.world, self.local = dist_env()
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — the MSM engine has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.L = eng._lib.lib
+        eng._lib.check(self.L.b200msm_init(self.local, 1), "init")
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.peak = eng.imad_peak()
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allmax(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def allok(self, ok):
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device=self.dev)
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+
+class Case:
+    """One MSM over the ranks: every rank holds `n` synthetic points (seeded per rank) in HBM, computes
+    its partial, the partials are all-gathered over NCCL and rank 0 adds them.  `n` per rank is the
+    caller's choice: fixed per GPU (weak scaling) or total/world (strong scaling)."""
+
+    def __init__(self, cx, g2, n, tag, canon=None):
+        import numpy as np
+
+        torch, eng = cx.torch, cx.eng
+        self.cx, self.g2, self.n, self.np = cx, int(g2), n, np
+        self.G = eng.G2 if g2 else eng.G1
+        self.grp = eng.G2Projective if g2 else eng.G1Projective
+        self.aw, self.jw = (24, 36) if g2 else (12, 18)
+        self.seed_b = SEED_BASES + 7919 * tag + 1000003 * cx.rank
+        self.seed_s = SEED_SCALARS + 7919 * tag + 1000003 * cx.rank
+        self.bases = torch.empty((n, self.aw), dtype=torch.int64, device=cx.dev)
+        self.scalars = torch.empty((n, 4), dtype=torch.int64, device=cx.dev)
+        eng.synth_bases_device(self.G, self.seed_b, n, self.bases.data_ptr(), cx.stream)
+        self.mont = canon is None
+        self.canon = canon
+        if canon is None:
+            eng.synth_scalars_device(self.seed_s, n, True, self.scalars.data_ptr(), cx.stream)  # Montgomery: what `msm` receives
+        else:
+            self.scalars.copy_(torch.from_numpy(canon.view(np.int64)))
+        self.partial = torch.zeros(self.jw, dtype=torch.int64, device=cx.dev)
+        self.gathered = torch.zeros((cx.world, self.jw), dtype=torch.int64, device=cx.dev)
+        self.result = torch.zeros(self.jw, dtype=torch.int64, device=cx.dev)
+        self.table = None
+        torch.cuda.synchronize()
+
+    def combine(self):
+        cx = self.cx
+        if cx.world > 1:
+            cx.dist.all_gather_into_tensor(self.gathered.view(-1), self.partial)
+            if cx.rank == 0:
+                cx.eng.sum_partials_device(self.G, self.gathered.data_ptr(), cx.world, self.result.data_ptr(), cx.stream)
+        else:
+            self.result.copy_(self.partial)
+
+    def step_device(self, table=False):
+        cx = self.cx
+        if table:
+            cx.eng.run_table_device(self.G, self.table["t"].data_ptr(), self.n, self.table["c"], self.scalars.data_ptr(), self.n, self.mont,
+                                    self.partial.data_ptr(), cx.stream)
+        else:
+            cx.eng.run_device(self.G, self.bases.data_ptr(), self.scalars.data_ptr(), self.n, self.mont, self.partial.data_ptr(), cx.stream)
+        self.combine()
+
+    def time_device(self, steps, warmup, table=False):
+        """CUDA events around every step on torch's current stream (the stream the MSM is launched on), L2 flushed
+        between steps outside the events, max over ranks. Returns (ms, phases of this rank, launches per step)."""
+        cx, torch = self.cx, self.cx.torch
+        for _ in range(warmup):
+            cx.flush.zero_()
+            self.step_device(table)
+        cx.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        launches0 = cx.L.b200msm_launch_count()
+        phases = []
+        for k in range(steps):
+            cx.flush.zero_()                   # L2 flush between steps, outside the per-step events
+            ev[k][0].record()
+            self.step_device(table)
+            ev[k][1].record()
+            ev[k][1].synchronize()
+            phases.append(cx.eng.last_phase_ms())
+        cx.barrier()
+        launches = (cx.L.b200msm_launch_count() - launches0) / steps
+        ms = cx.allmax(sum(a.elapsed_time(b) for a, b in ev) / steps)
+        ph = {k: sum(p[k] for p in phases) / len(phases) for k in phases[0] if k != "valid"}
+        return ms, ph, launches
+
+    def expected_partial(self):
+        from oracle import cref
+
+        sc = self.canon if self.canon is not None else cref.synth_scalars(self.seed_s, self.n, False)
+        return cref.msm_by_dlog(self.g2, self.seed_b, sc)
+
+    def check(self, extra_totals=()):
+        """this rank's partial against the known-discrete-log closed form; on rank 0 the combined result against the
+        sum of all ranks' expected partials, and every array in `extra_totals` against the combined result"""
+        from oracle import cref
+
+        cx, np, torch = self.cx, self.np, self.cx.torch
+        exp = self.expected_partial()
+        ok = cref.affine_equal(self.g2, self.partial.cpu().numpy().view(np.uint64), exp)
+        if cx.world > 1:
+            exp_all = [torch.zeros(self.jw, dtype=torch.int64, device=cx.dev) for _ in range(cx.world)]
+            cx.dist.all_gather(exp_all, torch.from_numpy(exp.view(np.int64)).to(cx.dev))
+        if cx.rank == 0:
+            total = self.result.cpu().numpy().view(np.uint64)
+            exp_total = exp
+            if cx.world > 1:
+                exp_total = np.zeros(self.jw, dtype=np.uint64)
+                for e in exp_all:
+                    exp_total = cref.add(self.g2, exp_total, e.cpu().numpy().view(np.uint64))
+            ok = ok and cref.affine_equal(self.g2, total, exp_total)
+            for x in extra_totals:
+                ok = ok and x is not None and cref.affine_equal(self.g2, x, exp_total)
+        return cx.allok(ok)
+
+    # ---- end to end: the reference-facing call with HOST buffers, H2D + D2H inside ----
+    def host_buffers(self, pinned):
+        torch, np = self.cx.torch, self.np
+        if pinned:
+            hb = torch.empty((self.n, self.aw), dtype=torch.int64, pin_memory=True)
+            hs = torch.empty((self.n, 4), dtype=torch.int64, pin_memory=True)
+            hb.copy_(self.bases); hs.copy_(self.scalars)
+            torch.cuda.synchronize()
+            return hb, hs, hb.numpy().view(np.uint64), hs.numpy().view(np.uint64)
+        hb_np = self.bases.cpu().numpy().view(np.uint64).copy()      # ordinary pageable memory, as a Rust Vec is
+        hs_np = self.scalars.cpu().numpy().view(np.uint64).copy()
+        return None, None, hb_np, hs_np
+
+    def time_e2e(self, steps, warmup, call):
+        """`call()` → this rank's partial as host limbs (through the host-buffer C-ABI); partials → device,
+        NCCL all-gather, final addition on rank 0, result read back. Wall clock bracketed by barriers, max over ranks."""
+        cx, torch, np = self.cx, self.cx.torch, self.np
+        hpart = torch.zeros(self.jw, dtype=torch.int64, pin_memory=True)
+
+        def step():
+            out = call()
+            if cx.world > 1:
+                hpart.numpy().view(np.uint64)[:] = out
+                self.partial.copy_(hpart, non_blocking=True)
+                cx.dist.all_gather_into_tensor(self.gathered.view(-1), self.partial)
+                if cx.rank == 0:
+                    cx.eng.sum_partials_device(self.G, self.gathered.data_ptr(), cx.world, self.result.data_ptr(), cx.stream)
+                    return self.result.cpu().numpy().view(np.uint64)
+                torch.cuda.synchronize()
+            return out
+
+        for _ in range(max(1, warmup)):
+            out = step()
+        cx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = step()
+        cx.barrier()
+        return cx.allmax((time.perf_counter() - t0) * 1e3 / steps), (out.copy() if cx.rank == 0 else None)
+
+
+def side_steps(args):
+    return min(args.steps, 5), 3
+
+
+def block_msm(cx, args, g2, n_total, tag, name):
+    """A BASELINE config as a strong-scaling block: an n_total-point MSM sharded evenly over the ranks."""
+    steps, warmup = side_steps(args)
+    lo, hi = n_total * cx.rank // cx.world, n_total * (cx.rank + 1) // cx.world
+    case = Case(cx, g2, hi - lo, tag)
+    ms, ph, _ = case.time_device(steps, warmup)
+    plan = cx.eng.last_plan()
+    total_dev = case.result.cpu().numpy().view(case.np.uint64).copy() if cx.rank == 0 else None
+    _, _, hb_np, hs_np = keep = case.host_buffers(True)
+    e2e_ms, e2e_out = case.time_e2e(steps, warmup, lambda: case.grp.msm(hb_np, hs_np))
+    case.step_device()
+    cx.barrier()
+    ok = case.check((total_dev, e2e_out))
+    del keep
+    c, W, fp_total, _ = work_model(n_total, g2)
+    out = {"workload": f"{'G2' if g2 else 'G1'} MSM 2^{int(math.log2(n_total))} points sharded over {cx.world} GPU(s) ({hi - lo} per GPU)",
+           "scaling": "strong", "ms": ms, "points_per_s": n_total / (ms * 1e-3), "e2e_ms": e2e_ms,
+           "e2e_h2d_bytes_per_step": n_total * (case.aw * 8 + 32), "parity_ok": ok, "steps": steps, "warmup": warmup,
+           "engine_plan_per_gpu": plan, "phases_ms_rank0": {k: round(v, 4) for k, v in ph.items()},
+           "whole_msm_frac_of_imad_peak": fp_total * FPMUL_IMAD / (ms * 1e-3) / (cx.peak["imad_per_s"] * cx.world),
+           "canonical_window_bits": c, "canonical_windows": W, "algorithmic_imad": fp_total * FPMUL_IMAD}
+    del case
+    cx.torch.cuda.empty_cache()
+    return out
+
+
+def witness_scalars(seed, n):
+    """≈40 % zeros, ≈20 % ones, ≈10 % below 2^32, rest uniform (canonical form)"""
+    import numpy as np
+
+    from oracle import cref
+
+    rng = np.random.default_rng(seed & 0xffffffff)
+    u = rng.random(n)
+    canon = cref.synth_scalars(seed, n, False)
+    small = rng.integers(0, 1 << 32, size=n, dtype=np.uint64)
+    canon[u < 0.7] = 0
+    canon[(u >= 0.4) & (u < 0.6), 0] = 1
+    mid = (u >= 0.6) & (u < 0.7)
+    canon[mid, 0] = small[mid]
+    return canon
+
+
+def block_groth16(cx, args, logn, scalars_kind, lanes=4, table=False, steps=None, warmup=3):
+    """BASELINE.json configs[4]: a Groth16-prover-shaped batch — three G1 MSMs and one G2 MSM of
+    2^logn points each, issued back to back on `lanes` engine lanes, every MSM sharded over the ranks."""
+    torch, eng, L = cx.torch, cx.eng, cx.L
+    from oracle import cref
+    import numpy as np
+
+    if steps is None:
+        steps, warmup = side_steps(args)
+    n_total = 1 << logn
+    lo, hi = n_total * cx.rank // cx.world, n_total * (cx.rank + 1) // cx.world
+    n = hi - lo
+    cases, nonzero = [], 0.0
+    for k, g2 in enumerate((1, 0, 0, 0)):  # G2 first: the tail left exposed at the end is a G1 one
+        canon = None
+        if scalars_kind == "witness":
+            canon = witness_scalars(SEED_SCALARS + 7919 * (40 + k) + 1000003 * cx.rank, n)
+            nonzero_k = cx.allsum(count_nonzero_booth_digits(canon, work_model(n_total, g2)[0]))
+        else:
+            c, W, _, _ = work_model(n_total, g2)
+            nonzero_k = n_total * W * (1 - 2.0 ** -c)
+        case = Case(cx, g2, n, 40 + k, canon)
+        if table:  # resident proving key: fixed-base window table per MSM, built once outside the timed region
+            tc, tw = eng.table_plan(g2, n)
+            t = torch.empty((tw, n, case.aw), dtype=torch.int64, device=cx.dev)
+            t[0].copy_(case.bases)
+            eng.table_build_device(g2, t.data_ptr(), n, tc, t.data_ptr(), cx.stream)
+            case.table = {"c": tc, "t": t}
+        cases.append((case, nonzero_k))
+    torch.cuda.synchronize()
+    lanes = max(1, min(lanes, len(cases)))
+    lane_streams = [torch.cuda.Stream(device=cx.dev) for _ in range(lanes)] if lanes > 1 else []
+
+    def step():
+        # the four MSMs go out on `lanes` engine lanes / streams (b200msm_set_lane): the latency-bound tail of one
+        # overlaps the accumulation of the next; the partials are gathered once all four are in
+        cur = torch.cuda.current_stream()
+        for k, (case, _) in enumerate(cases):
+            st = cx.stream
+            if lanes > 1:
+                L.b200msm_set_lane(k % lanes)
+                lane_streams[k % lanes].wait_stream(cur)
+                st = lane_streams[k % lanes].cuda_stream
+            if case.table:
+                eng.run_table_device(case.G, case.table["t"].data_ptr(), n, case.table["c"], case.scalars.data_ptr(), n, case.mont,
+                                     case.partial.data_ptr(), st)
+            else:
+                eng.run_device(case.G, case.bases.data_ptr(), case.scalars.data_ptr(), n, case.mont, case.partial.data_ptr(), st)
+        if lanes > 1:
+            L.b200msm_set_lane(0)
+            for ls in lane_streams:
+                cur.wait_stream(ls)
+        for case, _ in cases:
+            case.combine()
+
+    for _ in range(warmup):
+        step()
+    cx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    e1.synchronize()
+    ms = cx.allmax(e0.elapsed_time(e1) / steps)
+    ok = True
+    for case, _ in cases:
+        ok = case.check() and ok
+    imad_uniform = (3 * work_model(n_total, False)[2] + work_model(n_total, True)[2]) * FPMUL_IMAD
+    imad = sum(work_model_counted(nz, n_total, case.g2) for case, nz in cases) * FPMUL_IMAD
+    peak = cx.peak["imad_per_s"] * cx.world
+    out = {"workload": f"3xG1 + 1xG2 MSM at 2^{logn} points each, sharded over {cx.world} GPU(s), {scalars_kind} scalars",
+           "ms_per_batch": ms, "steps": steps, "warmup": warmup, "lanes": lanes, "parity_ok": ok,
+           "bases": "resident fixed-base window tables (built once)" if table else "resident affine bases",
+           "algorithmic_imad": imad,
+           "numerator": "SURVEY 8d work model at the canonical c*, accumulate term = the non-zero Booth digits of THESE scalars (counted)"
+           if scalars_kind == "witness" else "SURVEY 8d work model at the canonical c*, uniform scalars",
+           "frac_of_imad_peak": imad / (ms * 1e-3) / peak,
+           "uniform_model_imad": imad_uniform}
+    del cases
+    torch.cuda.empty_cache()
+    return out
+
+
+def block_single_process(args, n_gpus):
+    """The path a Rust `msm` takes on an 8-GPU box: ONE process, b200msm_init(0, N), host buffers in,
+    the library shards over the N GPUs (one host worker thread per device, partials to device 0 by peer
+    copy).  Runs as a child process of rank 0 while the other ranks wait at a barrier (their GPUs idle)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--workload", "single_process", "--gpus", str(n_gpus),
+           "--steps", str(min(args.steps, 5)), "--warmup", "3"]
+    drop = ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "MASTER_ADDR", "MASTER_PORT",
+            "TORCHELASTIC_RUN_ID")
+    env = {k: v for k, v in os.environ.items() if k not in drop}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        for line in reversed(r.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"error": (r.stderr or r.stdout)[-400:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
+def run_single_process(args):
+    """child of block_single_process (also usable alone: --workload single_process --gpus N)"""
     import numpy as np
     import torch
 
     import ark_blst_b200 as eng
+    from oracle import cref
 
-    rank, world, local = dist_env()
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the MSM engine has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
     L = eng._lib.lib
-    eng._lib.check(L.b200msm_init(local, 1), "init")
+    N = args.gpus
+    eng._lib.check(L.b200msm_init(0, N), "init")
+    out = {"api": f"one process: b200msm_init(0, {N}) then b200msm_g1 / b200msm_run(host buffers); sharding, peer gather and final addition inside the library",
+           "devices_bound": L.b200msm_device_count()}
+    torch.cuda.set_device(0)
+    for name, g2, logn in (("g1_2p24", 0, args.logn or 24), ("g2_2p20", 1, 20)):
+        n = 1 << logn
+        aw = 24 if g2 else 12
+        grp = eng.G2Projective if g2 else eng.G1Projective
+        db = torch.empty((n, aw), dtype=torch.int64, device="cuda:0")
+        ds = torch.empty((n, 4), dtype=torch.int64, device="cuda:0")
+        eng.synth_bases_device(g2, SEED_BASES + 99, n, db.data_ptr(), 0)
+        eng.synth_scalars_device(SEED_SCALARS + 99, n, True, ds.data_ptr(), 0)
+        torch.cuda.synchronize()
+        hb = torch.empty((n, aw), dtype=torch.int64, pin_memory=True); hb.copy_(db)
+        hs = torch.empty((n, 4), dtype=torch.int64, pin_memory=True); hs.copy_(ds)
+        torch.cuda.synchronize()
+        del db, ds
+        torch.cuda.empty_cache()
+        exp = cref.msm_by_dlog(g2, SEED_BASES + 99, cref.synth_scalars(SEED_SCALARS + 99, n, False))
+        hb_np, hs_np = hb.numpy().view(np.uint64), hs.numpy().view(np.uint64)
+
+        def timeit(call):
+            for _ in range(args.warmup):
+                r = call()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                r = call()
+            return (time.perf_counter() - t0) * 1e3 / args.steps, bool(cref.affine_equal(g2, r, exp))
+
+        res = {"points": n}
+        res["e2e_pinned_ms"], ok1 = timeit(lambda: grp.msm(hb_np, hs_np))
+        pb, ps = hb_np.copy(), hs_np.copy()
+        res["e2e_pageable_ms"], ok2 = timeit(lambda: grp.msm(pb, ps))
+        del pb
+        rb = eng.ResidentBases(grp, hb_np)
+        res["resident_bases_e2e_ms"], ok3 = timeit(lambda: rb.msm(hs_np))
+        res["resident_bases_pageable_scalars_ms"], ok3b = timeit(lambda: rb.msm(ps))
+        ok4 = True
+        if not g2:
+            rb.precompute()
+            res["resident_table_e2e_ms"], ok4 = timeit(lambda: rb.msm(hs_np))
+        rb.close()
+        res["parity_ok"] = ok1 and ok2 and ok3 and ok3b and ok4
+        res["h2d_bytes_per_step"] = n * (aw * 8 + 32)
+        out[name] = res
+        del hb, hs
+    L.b200msm_shutdown()
+    print(json.dumps(out))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+
+    cx = Ctx(args)
+    torch, eng, L = cx.torch, cx.eng, cx.L
+    rank, world = cx.rank, cx.world
+    blocks = set(ALL_BLOCKS if args.blocks == "all" else [b for b in args.blocks.split(",") if b and b != "headline"])
 
     g2 = args.group == "g2"
-    G = eng.G2 if g2 else eng.G1
     n = 1 << args.logn
     n_total = n * world
-    aw, jw = (24, 36) if g2 else (12, 18)
-    seed_b = SEED_BASES + 1000003 * rank
-    seed_s = SEED_SCALARS + 1000003 * rank
-    stream = torch.cuda.current_stream().cuda_stream
-
-    bases = torch.empty((n, aw), dtype=torch.int64, device=dev)
-    scalars = torch.empty((n, 4), dtype=torch.int64, device=dev)
-    eng.synth_bases_device(G, seed_b, n, bases.data_ptr(), stream)
-    eng.synth_scalars_device(seed_s, n, True, scalars.data_ptr(), stream)  # Montgomery: what `msm` receives
-    torch.cuda.synchronize()
-
-    peak = eng.imad_peak() if rank == 0 else None
-    partial = torch.zeros(jw, dtype=torch.int64, device=dev)
-    gathered = torch.zeros((world, jw), dtype=torch.int64, device=dev)
-    result = torch.zeros(jw, dtype=torch.int64, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    tbl = {}
-
-    def step_device(table=False):
-        if table:
-            eng.run_table_device(G, tbl["t"].data_ptr(), n, tbl["c"], scalars.data_ptr(), n, True, partial.data_ptr(), stream)
-        else:
-            eng.run_device(G, bases.data_ptr(), scalars.data_ptr(), n, True, partial.data_ptr(), stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), partial)
-            if rank == 0:
-                eng.sum_partials_device(G, gathered.data_ptr(), world, result.data_ptr(), stream)
-        else:
-            result.copy_(partial)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     L.b200msm_set_profiling(1)
-    for _ in range(args.warmup):
-        flush.zero_()
-        step_device()
-    barrier()
+    head = Case(cx, g2, n, 0)
+    aw, jw = head.aw, head.jw
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(cx.local)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches0 = L.b200msm_launch_count()
-    phases = []
-    barrier()
+    cx.barrier()
     t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.zero_()                      # L2 flush between steps, outside the per-step events
-        ev[k][0].record()
-        step_device()
-        ev[k][1].record()
-        ev[k][1].synchronize()
-        phases.append(eng.last_phase_ms())
-    plan = eng.last_plan()
-    barrier()
+    dev_ms, ph, launches = head.time_device(args.steps, args.warmup)
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
-    launches = (L.b200msm_launch_count() - launches0) / args.steps
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
+    plan = eng.last_plan()
+    total_dev = head.result.cpu().numpy().view(np.uint64).copy() if rank == 0 else None
+    my_partial_ok_later = head.partial.clone()
 
-    # ---- e2e: the reference-facing call with HOST buffers (pinned), H2D + D2H inside ----
-    hb = torch.empty((n, aw), dtype=torch.int64, pin_memory=True)
-    hs = torch.empty((n, 4), dtype=torch.int64, pin_memory=True)
-    hb.copy_(bases); hs.copy_(scalars)
-    torch.cuda.synchronize()
-    hb_np, hs_np = hb.numpy().view(np.uint64), hs.numpy().view(np.uint64)
-    grp = eng.G2Projective if g2 else eng.G1Projective
-    hpart = torch.zeros(jw, dtype=torch.int64, pin_memory=True)
-
-    def step_e2e():
-        out = grp.msm(hb_np, hs_np)                         # b200msm_g1(host, host) → 144 B back
-        if world > 1:
-            hpart.numpy().view(np.uint64)[:] = out
-            partial.copy_(hpart, non_blocking=True)
-            dist.all_gather_into_tensor(gathered.view(-1), partial)
-            if rank == 0:
-                eng.sum_partials_device(G, gathered.data_ptr(), world, result.data_ptr(), stream)
-                return result.cpu().numpy().view(np.uint64)
-            torch.cuda.synchronize()
-        return out
-
-    for _ in range(max(1, args.warmup)):
-        e2e_out = step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_out = step_e2e()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    # ---- e2e: the reference-facing call with HOST buffers, H2D + D2H inside ----
+    hb, hs, hb_np, hs_np = head.host_buffers(True)
+    e2e_ms, e2e_out = head.time_e2e(args.steps, args.warmup, lambda: head.grp.msm(hb_np, hs_np))
     clocks = sampler.stop() if rank == 0 else None
-
-    my_partial = partial.cpu().numpy().view(np.uint64)
+    _, _, pb_np, ps_np = head.host_buffers(False)
+    e2e_pg_ms, e2e_pg_out = head.time_e2e(min(args.steps, 10), 3, lambda: head.grp.msm(pb_np, ps_np))
+    del pb_np
 
     # ---- resident bases with a fixed-base window table (b200msm_bases_precompute): the prover
     # shape — the proving key's bases stay on the device, only scalars arrive per MSM.  Reported
     # beside the headline, never instead of it: `value` and `e2e` above take fresh bases per call.
-    table_info = None
+    table_info, extra = None, [total_dev, e2e_out, e2e_pg_out]
     if not args.no_table:
-        c_t, W_t = eng.table_plan(G, n)
-        tbl["c"] = c_t
-        tbl["t"] = torch.empty((W_t, n, aw), dtype=torch.int64, device=dev)
-        tbl["t"][0].copy_(bases)
+        c_t, W_t = eng.table_plan(head.G, n)
+        t = torch.empty((W_t, n, aw), dtype=torch.int64, device=cx.dev)
+        t[0].copy_(head.bases)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        eng.table_build_device(G, tbl["t"].data_ptr(), n, c_t, tbl["t"].data_ptr(), stream)
+        eng.table_build_device(head.G, t.data_ptr(), n, c_t, t.data_ptr(), cx.stream)
         torch.cuda.synchronize()
         build_ms = (time.perf_counter() - t0) * 1e3
-        for _ in range(args.warmup):
-            flush.zero_()
-            step_device(True)
-        barrier()
-        tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        tphases = []
-        for k in range(args.steps):
-            flush.zero_()
-            tev[k][0].record()
-            step_device(True)
-            tev[k][1].record()
-            tev[k][1].synchronize()
-            tphases.append(eng.last_phase_ms())
-        barrier()
-        t = torch.tensor([sum(a.elapsed_time(b) for a, b in tev) / args.steps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tbl_ms = float(t.item())
-        tbl_partial = partial.cpu().numpy().view(np.uint64).copy()
-        tbl_total = result.cpu().numpy().view(np.uint64).copy() if rank == 0 else None
+        head.table = {"c": c_t, "t": t}
+        tbl_ms, tph, _ = head.time_device(args.steps, args.warmup, table=True)
+        extra.append(head.result.cpu().numpy().view(np.uint64).copy() if rank == 0 else None)
         # end to end: b200msm_bases_upload + b200msm_bases_precompute once, then b200msm_run(host scalars) per MSM
-        rb = eng.ResidentBases(grp, hb_np)
-
-        def step_e2e_resident():
-            out = rb.msm(hs_np, montgomery=True)
-            if world > 1:
-                hpart.numpy().view(np.uint64)[:] = out
-                partial.copy_(hpart, non_blocking=True)
-                dist.all_gather_into_tensor(gathered.view(-1), partial)
-                if rank == 0:
-                    eng.sum_partials_device(G, gathered.data_ptr(), world, result.data_ptr(), stream)
-                    return result.cpu().numpy().view(np.uint64)
-                torch.cuda.synchronize()
-            return out
-
-        def time_resident():
-            for _ in range(max(1, args.warmup)):
-                out = step_e2e_resident()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                out = step_e2e_resident()
-            barrier()
-            tt = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            return out, float(tt.item())
-
-        res_e2e_out, res_e2e_ms = time_resident()      # resident bases as uploaded (no table): scalars H2D only
+        rb = eng.ResidentBases(head.grp, hb_np)
+        res_e2e_ms, res_out = head.time_e2e(args.steps, args.warmup, lambda: rb.msm(hs_np, montgomery=True))
+        res_pg_ms, res_pg_out = head.time_e2e(min(args.steps, 10), 3, lambda: rb.msm(ps_np, montgomery=True))
         rb.precompute(c_t)
-        tbl_e2e_out, tbl_e2e_ms = time_resident()      # the same handle as a fixed-base window table
-        t = torch.tensor([tbl_e2e_ms], dtype=torch.float64, device=dev)
+        tbl_e2e_ms, tbl_out = head.time_e2e(args.steps, args.warmup, lambda: rb.msm(hs_np, montgomery=True))
         rb.close()
-        tph = {k: sum(p[k] for p in tphases) / len(tphases) for k in tphases[0] if k != "valid"}
+        extra += [res_out, res_pg_out, tbl_out]
         table_info = {"ms_per_msm": tbl_ms, "points_per_s": n_total / (tbl_ms * 1e-3), "window_bits": c_t, "windows": W_t,
                       "table_bytes_per_gpu": W_t * n * aw * 8, "build_ms_once": build_ms,
                       "phases_ms": {k: round(v, 4) for k, v in tph.items()},
-                      "e2e_ms": float(t.item()), "e2e_h2d_bytes_per_step": n * 32 * world,
-                      "e2e_ms_resident_without_table": res_e2e_ms,
+                      "e2e_ms": tbl_e2e_ms, "e2e_h2d_bytes_per_step": n * 32 * world,
+                      "e2e_ms_resident_without_table": res_e2e_ms, "e2e_ms_resident_without_table_pageable_scalars": res_pg_ms,
                       "api": "b200msm_bases_upload + b200msm_bases_precompute once; per MSM b200msm_run(handle, host scalars) "
                              "(device figure: b200msm_run_table_device)"}
+        head.table = None
+        del t
+        torch.cuda.empty_cache()
 
-    # ---- parity of what was timed (the oracle is the checker only) + CPU baseline ----
+    # ---- parity of what was timed (the oracle is the checker only) ----
     from oracle import cref
 
-    exp_partial = cref.msm_by_dlog(int(g2), seed_b, cref.synth_scalars(seed_s, n, False))
-    ok = cref.affine_equal(int(g2), my_partial, exp_partial)
-    okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
-    if world > 1:
-        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-        exp_all = [torch.zeros(jw, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(exp_all, torch.from_numpy(exp_partial.view(np.int64)).to(dev))
-    if table_info is not None:
-        okt2 = torch.tensor([1 if cref.affine_equal(int(g2), tbl_partial, exp_partial) else 0], dtype=torch.int32, device=dev)
-        if world > 1:
-            dist.all_reduce(okt2, op=dist.ReduceOp.MIN)
-        okt = torch.minimum(okt, okt2)
-    parity = bool(okt.item())
-    if rank == 0:
-        total = result.cpu().numpy().view(np.uint64)
-        if world > 1:
-            exp_total = np.zeros(jw, dtype=np.uint64)
-            for e in exp_all:
-                exp_total = cref.add(int(g2), exp_total, e.cpu().numpy().view(np.uint64))
-            parity = parity and cref.affine_equal(int(g2), total, exp_total)
-        parity = parity and cref.affine_equal(int(g2), e2e_out, total)
-        if table_info is not None:
-            parity = parity and cref.affine_equal(int(g2), tbl_total, total) and cref.affine_equal(int(g2), tbl_e2e_out, total)
-            parity = parity and cref.affine_equal(int(g2), res_e2e_out, total)
-            table_info["frac_of_plain_msm_imad"] = None  # filled below
+    head.step_device()
+    cx.barrier()
+    parity = head.check(extra)
+    parity = parity and cx.allok(cref.affine_equal(int(g2), my_partial_ok_later.cpu().numpy().view(np.uint64), head.expected_partial()))
 
-        cpu = None
-        if world == 1 and not args.no_cpu:
+    # ---- CPU baseline: rank 0 at N=1 only, the full headline workload on every host core ----
+    cpu = None
+    c0_cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = cref.ncores()
+        best = None
+        reps = 2 if args.logn <= 20 else 1
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            cpu_out = cref.msm(int(g2), hb_np, hs_np, 1, nthreads=cores)
+            dt = (time.perf_counter() - t0) * 1e3
+            best = dt if best is None else min(best, dt)
+        parity = parity and cref.affine_equal(int(g2), cpu_out, total_dev)
+        cpu = {"value": best, "unit": "ms", "cores": cores, "kind": "port",
+               "sample": f"the full 2^{args.logn}-point workload, best of {reps} runs, same inputs as the GPU step",
+               "what": cpu_what(cref)}
+    del hb, hs
+    extra_blocks = {}
+    L.b200msm_set_profiling(0)
+
+    # ---- the other BASELINE configs, each a block of the same line ----
+    if "c0_2p16" in blocks:
+        steps, warmup = max(args.steps, 10), 3
+        case = Case(cx, 0, 1 << 16, 16)
+        # configs[0] is a single-GPU shape: every rank runs its own copy, rank 0's time is reported
+        world_save, cx.world, dist_save, cx.dist = cx.world, 1, cx.dist, None
+        L.b200msm_set_profiling(1)
+        ms16, ph16, _ = case.time_device(steps, warmup)
+        L.b200msm_set_profiling(0)
+        plan16 = eng.last_plan()
+        _, _, b16, s16 = keep = case.host_buffers(True)
+        e2e16, out16 = case.time_e2e(steps, warmup, lambda: case.grp.msm(b16, s16))
+        case.step_device()
+        ok16 = case.check((out16,))
+        blk = {"workload": "G1 MSM 2^16 random points/scalars (benches/group.rs:18-26 shape), one GPU", "ms": ms16, "e2e_ms": e2e16,
+               "parity_ok": ok16, "engine_plan": plan16, "phases_ms": {k: round(v, 4) for k, v in ph16.items()},
+               "whole_msm_frac_of_imad_peak": work_model(1 << 16, False)[2] * FPMUL_IMAD / (ms16 * 1e-3) / cx.peak["imad_per_s"]}
+        if rank == 0 and world_save == 1 and not args.no_cpu:
             cores = cref.ncores()
-            best = None
-            reps = 2 if args.logn <= 20 else 1
-            for _ in range(reps):
+            ts = []
+            for _ in range(4):
                 t0 = time.perf_counter()
-                cpu_out = cref.msm(int(g2), hb_np, hs_np, 1, nthreads=cores)
-                dt = (time.perf_counter() - t0) * 1e3
-                best = dt if best is None else min(best, dt)
-            parity = parity and cref.affine_equal(int(g2), cpu_out, total)
-            cpu = {"value": best, "unit": "ms", "cores": cores, "kind": "port",
-                   "sample": f"the full 2^{args.logn}-point workload, best of {reps} runs, same inputs as the GPU step",
-                   "what": "oracle/libmsm_ref.so: C restatement of blst 0.3.10 Pippenger (portable u128 Montgomery, "
-                           "no hand-written asm); real blst cannot be built here (Rust, no cargo)"}
+                cpu16 = cref.msm(0, b16, s16, 1, nthreads=cores)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            blk["cpu_ms"] = min(ts[1:])
+            blk["cpu_cores"] = cores
+            blk["cpu_what"] = "the same C port as cpu_baseline, full 2^16-point workload, best of 3 after one warm-up"
+            blk["parity_ok"] = blk["parity_ok"] and bool(cref.affine_equal(0, cpu16, out16))
+        cx.world, cx.dist = world_save, dist_save
+        blk["parity_ok"] = cx.allok(blk["parity_ok"])
+        extra_blocks["c0_2p16"] = blk
+        del case, keep
+        torch.cuda.empty_cache()
+    if "g2_2p20" in blocks:
+        extra_blocks["g2_2p20"] = block_msm(cx, args, True, 1 << 20, 20, "g2_2p20")
+    if "strong_2p24" in blocks:
+        extra_blocks["strong_2p24"] = block_msm(cx, args, False, 1 << 24, 24, "strong_2p24")
+    if "groth16_2p22" in blocks:
+        extra_blocks["groth16_2p22"] = {"uniform": block_groth16(cx, args, 22, "uniform"),
+                                        "witness_like": block_groth16(cx, args, 22, "witness")}
+    if "single_process" in blocks and world > 1:
+        cx.barrier()
+        sp = block_single_process(args, world) if rank == 0 else None
+        cx.barrier()
+        if rank == 0:
+            extra_blocks["single_process"] = sp
 
+    if rank == 0:
+        for b in extra_blocks.values():
+            for v in (b.values() if "parity_ok" not in b else [b]):
+                if isinstance(v, dict) and "parity_ok" in v:
+                    parity = parity and bool(v["parity_ok"])
         c, W, _, fpmul_acc = work_model(n, g2)            # what each GPU's accumulate kernel runs
         _, _, fpmul_total, _ = work_model(n_total, g2)     # single-problem numerator (SURVEY §8d)
-        ph = {k: sum(p[k] for p in phases) / len(phases) for k in phases[0] if k != "valid"}
         acc_s = ph["accumulate"] * 1e-3
-        imad_peak = peak["imad_per_s"]
+        imad_peak = cx.peak["imad_per_s"]
         achieved = fpmul_acc * FPMUL_IMAD / acc_s
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(f"k_accumulate_{args.group}_2^{args.logn}")
+                tj = json.load(open(tpath))
+                traffic = tj.get(f"k_accumulate_{args.group}_2^{args.logn}")
+                traffic_src = tj.get("source")
             except Exception:
                 traffic = None
         line = {
@@ -433,14 +810,15 @@ def run_ours(args):
                        "scalars": "uniform mod r, Montgomery form (VariableBaseMSM::msm)",
                        "bases": "random subgroup points k_i*G, affine, resident in HBM",
                        "l2": "flushed between steps (256 MiB memset, outside the per-step events)",
-                       "parity": "GPU result == (sum s_i k_i)*G and == CPU oracle result" if parity else "MISMATCH"},
+                       "parity": "every timed result == (sum s_i k_i)*G (known-discrete-log closed form) and == the CPU port's result" if parity else "MISMATCH"},
             "parity_ok": parity,
-            "wall_ms_per_step_incl_flush": wall_ms / args.steps,
+            "wall_ms_per_step_incl_flush": wall_ms / (args.steps + args.warmup),
             "phases_ms": {k: round(v, 4) for k, v in ph.items()},
             "roofline": {
-                "bound": "imad", "kernel": f"k_accumulate<{'fp2' if g2 else 'fp'}> (+heavy-bucket kernels)",
+                "bound": "imad", "kernel": f"bucket accumulation: k_accumulate<{'fp2' if g2 else 'fp'}> (+ heavy-bucket and batched-affine kernels of the same phase)",
                 "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
                 "frac": achieved / imad_peak, "traffic": traffic,
+                "traffic_source": traffic_src or "profiles/traffic.json: dram bytes of one ncu --set full capture of this kernel (a recorded constant, not measured in this run)",
                 "peak_source": "measured live by b200msm_imad_peak (mad.lo.u32 issue rate; MEASURED_PEAKS.json has no integer figure)",
                 "algorithmic_imad_per_launch": fpmul_acc * FPMUL_IMAD,
                 "kernel_ms": ph["accumulate"],
@@ -453,145 +831,41 @@ def run_ours(args):
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": n * (aw * 8 + 32) * world,
                     "d2h_bytes_per_step": jw * 8 * world, "points_per_s": n_total / (e2e_ms * 1e-3),
                     "api": "b200msm_g1/b200msm_g2(host bases, host scalars) via ark_blst_b200.G?Projective.msm, pinned host memory"},
+            "e2e_pageable": {"value": e2e_pg_ms, "unit": "ms", "steps": min(args.steps, 10),
+                             "api": "the same call from ordinary pageable host memory (numpy arrays; what a Rust Vec is)"},
             "resident_table": table_info,
+            **extra_blocks,
             "gpu_launches": launches,
             "clocks": clocks,
-            "imad_peak": peak,
+            "imad_peak": cx.peak,
         }
         if table_info is not None:  # same numerator as the headline (the plain MSM's algorithmic work at c*)
             table_info["frac_of_plain_msm_imad"] = fpmul_total * FPMUL_IMAD / (table_info["ms_per_msm"] * 1e-3) / (imad_peak * world)
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        cx.dist.barrier()
+        cx.dist.destroy_process_group()
     return 0
 
 
 def run_groth16(args):
-    """BASELINE.json configs[4]: a Groth16-prover-shaped batch — three G1 MSMs and one G2 MSM of
-    2^logn points each, issued back to back, every MSM sharded over the ranks (non-default mode:
-    `--workload groth16`, default logn 22). Device-resident inputs; one JSON line from rank 0."""
-    import numpy as np
-    import torch
-
-    import ark_blst_b200 as eng
-    from oracle import cref
-
-    rank, world, local = dist_env()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
-    L = eng._lib.lib
-    eng._lib.check(L.b200msm_init(local, 1), "init")
-    n_total = 1 << args.logn
-    lo, hi = n_total * rank // world, n_total * (rank + 1) // world
-    n = hi - lo
-    stream = torch.cuda.current_stream().cuda_stream
-    jobs = []  # (group, bases, scalars, seeds)
-    for k, g2 in enumerate((1, 0, 0, 0)):  # G2 first: the tail left exposed at the end is a G1 one
-        aw = 24 if g2 else 12
-        sb, ss = SEED_BASES + 7919 * k + 1000003 * rank, SEED_SCALARS + 7919 * k + 1000003 * rank
-        b = torch.empty((n, aw), dtype=torch.int64, device=dev)
-        s = torch.empty((n, 4), dtype=torch.int64, device=dev)
-        eng.synth_bases_device(g2, sb, n, b.data_ptr(), stream)
-        eng.synth_scalars_device(ss, n, True, s.data_ptr(), stream)
-        canon = None
-        if args.scalars == "witness":   # SURVEY §8d C4: ≈40 % zeros, ≈20 % ones, ≈10 % below 2^32, rest uniform (canonical form)
-            rng = np.random.default_rng(ss & 0xffffffff)
-            u = rng.random(n)
-            canon = cref.synth_scalars(ss, n, False)
-            small = rng.integers(0, 1 << 32, size=n, dtype=np.uint64)
-            canon[u < 0.7] = 0
-            canon[(u >= 0.4) & (u < 0.6), 0] = 1
-            mid = (u >= 0.6) & (u < 0.7)
-            canon[mid, 0] = small[mid]
-            s.copy_(torch.from_numpy(canon.view(np.int64)))
-        tc = 0
-        if args.table:  # resident proving key: fixed-base window table per MSM, built once outside the timed region
-            tc, tw = eng.table_plan(g2, n)
-            t = torch.empty((tw, n, aw), dtype=torch.int64, device=dev)
-            t[0].copy_(b)
-            eng.table_build_device(g2, t.data_ptr(), n, tc, t.data_ptr(), stream)
-            b = t
-        jobs.append((g2, b, s, sb, ss, torch.zeros(36 if g2 else 18, dtype=torch.int64, device=dev), tc, canon))
-    torch.cuda.synchronize()
-    peak = eng.imad_peak()["imad_per_s"] if rank == 0 else None
-
-    lanes = max(1, min(args.lanes, len(jobs)))
-    lane_streams = [torch.cuda.Stream(device=dev) for _ in range(lanes)] if lanes > 1 else []
-
-    def step():
-        # the four MSMs go out on `lanes` engine lanes / streams (b200msm_set_lane): the latency-bound tail of one
-        # overlaps the accumulation of the next; the partials are gathered once all four are in
-        cur = torch.cuda.current_stream()
-        for k, (g2, b, s, _, _, part, tc, _c) in enumerate(jobs):
-            st = stream
-            if lanes > 1:
-                L.b200msm_set_lane(k % lanes)
-                lane_streams[k % lanes].wait_stream(cur)
-                st = lane_streams[k % lanes].cuda_stream
-            if tc:
-                eng.run_table_device(g2, b.data_ptr(), n, tc, s.data_ptr(), n, _c is None, part.data_ptr(), st)
-            else:
-                eng.run_device(g2, b.data_ptr(), s.data_ptr(), n, _c is None, part.data_ptr(), st)
-        if lanes > 1:
-            L.b200msm_set_lane(0)
-            for ls in lane_streams:
-                cur.wait_stream(ls)
-        outs = []
-        for g2, b, s, _, _, part, tc, _c in jobs:
-            if world > 1:
-                gathered = torch.empty((world, part.numel()), dtype=torch.int64, device=dev)
-                dist.all_gather_into_tensor(gathered.view(-1), part)
-                if rank == 0:
-                    res = torch.zeros_like(part)
-                    eng.sum_partials_device(g2, gathered.data_ptr(), world, res.data_ptr(), stream)
-                    outs.append(res)
-            else:
-                outs.append(part)
-        return outs
-
-    for _ in range(args.warmup):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        outs = step()
-    e1.record()
-    e1.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    ok = True
-    for g2, b, s, sb, ss, part, _, canon in jobs:   # every rank checks its own partial against the dlog closed form
-        exp = cref.msm_by_dlog(g2, sb, canon if canon is not None else cref.synth_scalars(ss, n, False))
-        ok = ok and cref.affine_equal(g2, part.cpu().numpy().view(np.uint64), exp)
-    okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
-    if world > 1:
-        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-    if rank == 0:
-        imad = (3 * work_model(n_total, False)[2] + work_model(n_total, True)[2]) * FPMUL_IMAD
+    """`--workload groth16`: the configs[4] block alone, with its knobs (--logn, --scalars, --lanes, --table)."""
+    cx = Ctx(args)
+    blk = block_groth16(cx, args, args.logn, args.scalars, lanes=args.lanes, table=args.table, steps=args.steps, warmup=args.warmup)
+    if cx.rank == 0:
         print(json.dumps({
-            "metric": "Groth16-shaped batch: 3xG1 + 1xG2 MSM, ms per batch", "value": ms, "unit": "ms", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
+            "metric": "Groth16-shaped batch: 3xG1 + 1xG2 MSM, ms per batch", "value": blk["ms_per_batch"], "unit": "ms", "n_gpus": cx.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": blk["ms_per_batch"], "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32x12 Montgomery limbs (integer)", "data": "synthetic",
-            "config": {"workload": f"3xG1 + 1xG2 MSM at 2^{args.logn} points each, sharded over {world} GPU(s), {'witness-like' if args.scalars == 'witness' else 'uniform'} scalars",
-                       "lanes": lanes,
-                       "bases": "resident fixed-base window tables (b200msm_table_build_device, built once)" if args.table else "resident affine bases"},
-            "parity_ok": bool(okt.item()),
-            "roofline": {"bound": "imad", "achieved": imad / (ms * 1e-3) / 1e12, "peak": peak * world / 1e12, "unit": "TIMAD/s",
-                         "frac": imad / (ms * 1e-3) / (peak * world), "traffic": None, "algorithmic_imad": imad}}))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+            "config": {"workload": blk["workload"], "lanes": blk["lanes"], "bases": blk["bases"]},
+            "parity_ok": blk["parity_ok"],
+            "roofline": {"bound": "imad", "achieved": blk["algorithmic_imad"] / (blk["ms_per_batch"] * 1e-3) / 1e12,
+                         "peak": cx.peak["imad_per_s"] * cx.world / 1e12, "unit": "TIMAD/s",
+                         "frac": blk["frac_of_imad_peak"], "traffic": None, "algorithmic_imad": blk["algorithmic_imad"],
+                         "numerator": blk["numerator"]}}))
+    if cx.world > 1:
+        cx.dist.barrier()
+        cx.dist.destroy_process_group()
     return 0
 
 
@@ -610,14 +884,19 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--group", default="g1", choices=["g1", "g2"])
     ap.add_argument("--logn", type=int, default=None, help="log2 of points per GPU (default 20; groth16 workload: total points, default 22)")
-    ap.add_argument("--workload", default="msm", choices=["msm", "groth16"])
-    ap.add_argument("--ref-sample-logn", type=int, default=20, help="reference arm: points actually timed per step")
+    ap.add_argument("--workload", default="msm", choices=["msm", "groth16", "single_process"])
+    ap.add_argument("--blocks", default="all", help="comma list of the extra per-config blocks to run beside the headline "
+                                                    f"({', '.join(ALL_BLOCKS)}), 'all' or 'headline' (none)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--scalars", default="uniform", choices=["uniform", "witness"], help="groth16 workload: scalar distribution")
     ap.add_argument("--lanes", type=int, default=4, help="groth16 workload: engine lanes / streams the four MSMs are spread over (1 = back to back on one stream)")
     ap.add_argument("--table", action="store_true", help="groth16 workload: run every MSM against a resident fixed-base window table")
     ap.add_argument("--no-table", action="store_true", help="skip the resident-bases fixed-base-table leg")
     args = ap.parse_args()
+    if args.workload == "single_process":
+        if args.warmup < 3:
+            args.warmup = 3
+        return run_single_process(args)
     if args.logn is None:
         args.logn = 22 if args.workload == "groth16" else 20
     if args.warmup < 3 and args.impl == "b200":

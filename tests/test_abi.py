@@ -148,3 +148,20 @@ def test_planner_cpp_unit(tmp_path):
     subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_plan.cpp")], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_bench_counts_the_nonzero_digits_of_witness_like_scalars(cref):
+    """bench.py's Groth16 witness-like numerator counts the bucket additions actually needed (VERDICT r1 weak #9:
+    the uniform-scalar model printed frac 1.19 on scalars that are 70 % zeros and ones)"""
+    import bench
+
+    s = bench.witness_scalars(123, 3000)
+    for c in (13, 18):
+        W = -(-256 // c)
+        want = sum(1 for i in range(s.shape[0]) for w in range(W)
+                   if cref.lib().ref_booth_digit(cref._p(np.ascontiguousarray(s[i])), w, c) != 0)
+        assert bench.count_nonzero_booth_digits(s, c) == want
+    uni = cref.synth_scalars(5, 3000, False)
+    c, W, _, _ = bench.work_model(1 << 22, False)
+    assert bench.count_nonzero_booth_digits(s, c) < 0.45 * bench.count_nonzero_booth_digits(uni, c)
+    assert bench.work_model_counted(bench.count_nonzero_booth_digits(s, c), 1 << 22, False) < bench.work_model(1 << 22, False)[2]

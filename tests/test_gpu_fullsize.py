@@ -38,7 +38,7 @@ def test_synth_matches_oracle(eng, cref):
         assert np.array_equal(sc.cpu().numpy().view(np.uint64), cref.synth_scalars(456, n, False))
 
 
-@pytest.mark.parametrize("g2,logn", [(0, 16), (0, 20), (1, 18), (1, 20)])
+@pytest.mark.parametrize("g2,logn", [(0, 16), (0, 20), (0, 22), (0, 24), (1, 18), (1, 20), (1, 22)])
 def test_dlog_closed_form(eng, cref, g2, logn):
     """Σ sᵢ·(kᵢ·G) = (Σ sᵢkᵢ mod r)·G at BASELINE sizes"""
     import torch
@@ -49,6 +49,16 @@ def test_dlog_closed_form(eng, cref, g2, logn):
     got = _run(eng, torch, g2, bases, scalars, n, True)
     exp = cref.msm_by_dlog(g2, sb, cref.synth_scalars(ss, n, False))
     assert cref.affine_equal(g2, got, exp)
+    if logn >= 22:   # the largest sizes also through the canonical-BigInt entry (msm_bigint) and with GLV forced the other way
+        _, canon = _dev_inputs(eng, torch, g2, sb, ss, n, False)
+        L = eng._lib.lib
+        try:
+            assert L.b200msm_set_glv(1 if logn > 22 else 0) == 0
+            assert cref.affine_equal(g2, _run(eng, torch, g2, bases, canon, n, False), exp)
+        finally:
+            L.b200msm_set_glv(-1)
+    del bases, scalars
+    torch.cuda.empty_cache()
 
 
 def test_shard_sum_invariance_and_linearity(eng, cref):
