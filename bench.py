@@ -432,7 +432,9 @@ def block_msm(cx, args, g2, n_total, tag, name):
     steps, warmup = side_steps(args)
     lo, hi = n_total * cx.rank // cx.world, n_total * (cx.rank + 1) // cx.world
     case = Case(cx, g2, hi - lo, tag)
+    cx.L.b200msm_set_profiling(1)
     ms, ph, _ = case.time_device(steps, warmup)
+    cx.L.b200msm_set_profiling(0)
     plan = cx.eng.last_plan()
     total_dev = case.result.cpu().numpy().view(case.np.uint64).copy() if cx.rank == 0 else None
     _, _, hb_np, hs_np = keep = case.host_buffers(True)
