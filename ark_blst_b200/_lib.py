@@ -44,6 +44,8 @@ SIGNATURES = {
     "b200msm_set_window_bits": (ctypes.c_int, [ctypes.c_int]),
     "b200msm_set_glv": (ctypes.c_int, [ctypes.c_int]),
     "b200msm_set_heavy_factor": (ctypes.c_int, [ctypes.c_int]),
+    "b200msm_set_batch_affine": (ctypes.c_int, [ctypes.c_int]),
+    "b200msm_set_graphs": (ctypes.c_int, [ctypes.c_int]),
     "b200msm_set_lane": (ctypes.c_int, [ctypes.c_int]),
     "b200msm_host_register": (ctypes.c_int, [vp, ctypes.c_size_t]),
     "b200msm_host_unregister": (ctypes.c_int, [vp]),

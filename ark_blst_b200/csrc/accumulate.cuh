@@ -135,11 +135,12 @@ k_endo_table(const uint32_t *__restrict__ bases, size_t n, uint32_t *__restrict_
 // one thread per bucket rank: heavy ones claim a slot and a run of tasks of ≤ chunk entries
 static __global__ void __launch_bounds__(256)
 k_plan_heavy(const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, uint32_t nb, uint32_t heavy_thr,
-             uint32_t chunk, HeavyHeader *__restrict__ hdr, HeavyBucket *__restrict__ hb, HeavyTask *__restrict__ tasks) {
+             uint32_t chunk, int shift, HeavyHeader *__restrict__ hdr, HeavyBucket *__restrict__ hb, HeavyTask *__restrict__ tasks) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nb) return;
     uint32_t b = order[t];
-    uint32_t s = start[b], cnt = start[b + 1] - s;
+    // shift > 0: after batched-affine rounds (batch_affine.cuh) the bucket owns positions [start[b], start[b+1]) >> shift
+    uint32_t s = start[b] >> shift, cnt = (start[b + 1] >> shift) - s;
     if (cnt <= heavy_thr) return;
     uint32_t nt = (cnt + chunk - 1) / chunk;
     uint32_t slot = atomicAdd(&hdr->n_heavy, 1u);
@@ -182,6 +183,15 @@ k_heavy_tasks(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ v
         xyzz<F> acc;
         xyzz_set_inf(acc);
         for (uint32_t j = threadIdx.x; j < tk.len; j += THREADS) {
+            if (!vals) {                               // direct: the points themselves, as the batched-affine rounds left them
+                const uint32_t *p = bases + (size_t)(tk.offset + j) * (2 * W);
+                F x, y;
+                f_load(x, p);
+                if (f_word(x, 11) == 0xffffffffu) continue;   // the rounds' "empty" marker
+                f_load(y, p + W);
+                xyzz_madd(acc, x, y);
+                continue;
+            }
             uint32_t v = vals[tk.offset + j];
             uint32_t idx = v & 0x7fffffffu;
             const bool endo = idx >= n_pts;

@@ -26,6 +26,7 @@ using namespace b200msm;
 
 namespace b200msm {
 unsigned long long g_own_launches = 0;
+thread_local unsigned long long t_own_launches = 0;
 }
 
 namespace {
@@ -44,6 +45,9 @@ int fail(int code, const std::string &msg) {
                         std::string(#expr) + ": " + cudaGetErrorString(e__));                \
     } while (0)
 
+// (re)allocations of any device buffer of this library: cached graphs hold raw pointers into the arenas
+std::atomic<unsigned> g_arena_epoch{0};
+
 // grow-only device buffer
 struct DevBuf {
     void *p = nullptr;
@@ -54,6 +58,7 @@ struct DevBuf {
         p = nullptr;
         cap = 0;
         size_t want = bytes + bytes / 8 + 256;
+        g_arena_epoch++;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {
             p = nullptr;
@@ -63,13 +68,38 @@ struct DevBuf {
         return 0;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) { cudaFree(p); g_arena_epoch++; }
         p = nullptr;
         cap = 0;
     }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// Everything the launches of one pass depend on — also the key under which its CUDA graph is cached.
+struct PassArgs {
+    int group = 0, mont = 0;
+    const uint32_t *d_bases = nullptr, *d_scalars = nullptr;
+    uint32_t *d_out = nullptr;
+    size_t n = 0;
+    int c = 0, nwin = 0, glv = 0;          // plan; glv: 0 off, 1 on, 2 on with the unsigned top digit
+    uint32_t nbw = 0, nb = 0;
+    const void *tbl_p = nullptr;           // fixed-base table (or null)
+    size_t tbl_stride = 0;
+    int into = 0, finish = 1;
+    uint32_t heavy_thr = 0;
+    int R = 0;                             // batched-affine pairing rounds before the XYZZ accumulation
+    unsigned arena = 0;                    // DeviceCtx::arena_epoch the scratch pointers belong to
+};
+bool same_pass(const PassArgs &a, const PassArgs &b) { return memcmp(&a, &b, sizeof a) == 0; }
+
+// A pass seen for the second time with the same arguments is recorded as two CUDA graphs (run_pass)
+struct PassGraph {
+    PassArgs key;
+    cudaGraphExec_t prep = nullptr, main = nullptr;
+    unsigned long long last_use = 0;
+    unsigned long long launches_prep = 0, launches_main = 0;   // kernels inside, for b200msm_launch_count
+    int plan[4] = {0, 0, 0, 0};
+};
 struct TableRef {
     const void *p;     // window-major affine table on the device
     size_t stride;     // points per window
@@ -90,6 +120,12 @@ struct DeviceCtx {
     int fits_tbl_c[2] = {0, 0};
     DevBuf bases, scalars, digits, vals, start, cnt, ord, buckets, lvlR[2], lvlC[2], out;
     DevBuf hvy_hdr, hvy_buckets, hvy_tasks, hvy_partials, treeS[2], treeV[2], treeC[2], wsum, chunk_partials, norm_in, norm_out, tile_sums, size_hist, endo, tbl_tmp;
+    DevBuf ba_prefix, ba_T, ba_prefix2, ba_U, ba_pts[2];   // batched-affine rounds (batch_affine.cuh)
+    std::vector<PassGraph> graphs;   // CUDA graphs of passes seen before (run_pass)
+    std::vector<PassArgs> seen;
+    unsigned long long graph_clock = 0;
+    cudaStream_t cap_stream = nullptr;      // graphs are recorded on this stream (never executed on it)
+    unsigned arena_epoch() const { return g_arena_epoch.load(); }
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_slice[16] = {};  // per slice of a streamed MSM: scalars ready, bases ready
     double phase_ms[8] = {};
@@ -99,7 +135,7 @@ struct DeviceCtx {
     std::vector<DevBuf *> scratch() {
         return {&digits, &vals, &start, &cnt, &ord, &buckets,
                 &lvlR[0], &lvlR[1], &lvlC[0], &lvlC[1], &hvy_hdr, &hvy_buckets, &hvy_tasks, &hvy_partials, &treeS[0],
-                &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum};
+                &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum, &ba_prefix, &ba_T, &ba_prefix2, &ba_U, &ba_pts[0], &ba_pts[1]};
     }
     size_t scratch_bytes() {
         size_t s = 0;
@@ -108,7 +144,7 @@ struct DeviceCtx {
     }
     void release_all() {
         for (DevBuf *b : {&bases, &scalars, &digits, &vals, &start, &cnt, &ord, &buckets, &lvlR[0], &lvlR[1], &lvlC[0], &lvlC[1], &out, &hvy_hdr, &hvy_buckets,
-                          &hvy_tasks, &hvy_partials, &treeS[0], &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum, &chunk_partials, &norm_in, &norm_out, &tile_sums, &size_hist, &endo, &tbl_tmp})
+                          &hvy_tasks, &hvy_partials, &treeS[0], &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum, &chunk_partials, &norm_in, &norm_out, &tile_sums, &size_hist, &endo, &tbl_tmp, &ba_prefix, &ba_T, &ba_prefix2, &ba_U, &ba_pts[0], &ba_pts[1]})
             b->release();
     }
 };
@@ -125,6 +161,7 @@ struct Tun {
     size_t stream_min = 1u << 18;
     int heavy_factor = 0;  // a bucket is heavy above heavy_factor × the mean occupancy (see run_pass); 0 = automatic
     int batch_affine = -1; // -1 automatic, 0 never, 1..3 = pairwise batched-affine rounds before the XYZZ accumulation
+    bool graphs = true;    // record a pass seen twice as CUDA graphs and replay it
     unsigned epoch = 0;    // bumped by every setter that changes what a pass allocates (fit caches are keyed on it)
 };
 struct Share;
@@ -184,6 +221,7 @@ int make_ctx(int d, int lane, int sm_count, std::unique_ptr<DeviceCtx> &out) {
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_share, cudaEventDisableTiming));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
     int lo_pri = 0, hi_pri = 0;
     CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
     CUDA_TRY(cudaStreamCreateWithPriority(&c->tail_stream, cudaStreamNonBlocking, hi_pri));
@@ -199,6 +237,10 @@ void destroy_ctx(DeviceCtx &c) {
     cudaSetDevice(c.dev);
     cudaStreamSynchronize(c.stream);
     cudaStreamSynchronize(c.tail_stream);
+    for (auto &g : c.graphs) { cudaGraphExecDestroy(g.prep); cudaGraphExecDestroy(g.main); }
+    c.graphs.clear();
+    c.seen.clear();
+    cudaStreamDestroy(c.cap_stream);
     c.release_all();
     for (auto &ev : c.ev) cudaEventDestroy(ev);
     for (auto &ev : c.ev_slice) cudaEventDestroy(ev);
@@ -308,20 +350,17 @@ struct PassOpts {
     const Plan *plan = nullptr;
     bool into = false, finish = true;
 };
-int run_pass(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v, const void *d_scalars_v, size_t n, int mont, void *d_out_v,
-              cudaStream_t st, cudaEvent_t bases_ready = nullptr, const TableRef *tbl = nullptr, const PassOpts &po = PassOpts()) {
-    if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "group must be B200MSM_G1 or B200MSM_G2");
+// Plan + scratch reservation of one pass (may allocate: never inside a graph capture).
+int pass_prepare(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v, const void *d_scalars_v, size_t n, int mont,
+                 void *d_out_v, const TableRef *tbl, const PassOpts &po, PassArgs &pa) {
     const bool g2 = group == B200MSM_G2;
-    const uint32_t *d_bases = (const uint32_t *)d_bases_v, *d_scalars = (const uint32_t *)d_scalars_v;
-    uint32_t *d_out = (uint32_t *)d_out_v;
     const int W = g2 ? 24 : 12;                      // u32 words per field element
     const size_t PB = 4 * (size_t)W * sizeof(uint32_t);  // bytes per XYZZ point
-    if (n == 0 && !po.plan) {
-        CUDA_TRY(cudaMemsetAsync(d_out, 0, 3 * W * 4, st));
-        return 0;
-    }
+    memset(&pa, 0, sizeof pa);                       // (padding bytes too: the struct is compared bytewise)
+    pa.group = group; pa.mont = mont; pa.n = n;
+    pa.d_bases = (const uint32_t *)d_bases_v; pa.d_scalars = (const uint32_t *)d_scalars_v; pa.d_out = (uint32_t *)d_out_v;
+    pa.into = po.into; pa.finish = po.finish;
     Plan pl;
-    if (tbl) d_bases = (const uint32_t *)tbl->p;
     if (po.plan) pl = *po.plan;
     else if (tbl) {  // the table fixes the width
         pl.c = tbl->c;
@@ -329,18 +368,35 @@ int run_pass(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v, con
         pl.glv = pl.split = false;
         pl.nbw = 1u << (pl.c - 1);
         pl.nb = pl.nbw;                       // one bucket set shared by all windows
-        d_bases = (const uint32_t *)tbl->p;
     } else auto_plan(n, g2, tn.glv_mode, tn.window_override, pl);
+    if (tbl) { pa.d_bases = (const uint32_t *)tbl->p; pa.tbl_p = tbl->p; pa.tbl_stride = tbl->stride; }
+    pa.c = pl.c; pa.nwin = pl.nwin; pa.glv = pl.glv ? (pl.split ? 2 : 1) : 0; pa.nbw = pl.nbw; pa.nb = pl.nb;
     const int rwin = tbl ? 1 : pl.nwin;       // windows the reduction sees
-    cx.last_plan[0] = pl.c; cx.last_plan[1] = pl.nwin; cx.last_plan[2] = pl.glv ? (pl.split ? 2 : 1) : 0; cx.last_plan[3] = tbl ? 1 : 0;
+    cx.last_plan[0] = pl.c; cx.last_plan[1] = pl.nwin; cx.last_plan[2] = pa.glv; cx.last_plan[3] = tbl ? 1 : 0;
     const size_t entries = pl.glv ? 2 * n : n;  // per window
     const size_t m = entries * (size_t)pl.nwin;
-    const bool prof = tn.profiling;
-    int evi = 0;
-    auto mark = [&]() { if (prof) cudaEventRecord(cx.ev[evi++], st); };
+    // heavy buckets: one thread per bucket is the efficient shape (≈0.31 product-times per entry
+    // per warp vs ≈1 for the block-cooperative path), so a bucket only counts as heavy when its
+    // serial chain would be a visible fraction (≈8 %) of the whole accumulation — the kernel lasts
+    // ≈ m/175k bucket-entry times — or when it exceeds 3× the mean occupancy, whichever is larger.
+    // Buckets are taken in decreasing-size order, so the long chains start first.
+    // Worst-case list sizes follow from Σ counts = m.
+    // (table mode: the buckets the top window also feeds hold up to ≈2.3× the mean, so the factor is 4 there)
+    const uint32_t avg = (uint32_t)(((tbl ? m : entries) + pl.nbw - 1) / pl.nbw);
+    // batched-affine pairing rounds: they pay when a bucket holds enough entries for the pairs to be real additions
+    // (padding to 2^R entries per bucket is wasted slots) — measured crossover, see profiles/r02_experiments.md
+    int R = tn.batch_affine;
+    if (R < 0) R = avg >= 40 ? 2 : (avg >= 14 ? 1 : 0);
+    if (n == 0) R = 0;
+    pa.R = R;
+    const int hfac = tn.heavy_factor ? tn.heavy_factor : (tbl ? 4 : 3);
+    // after R rounds a bucket's run is 2^R times shorter and so is the whole accumulation: the threshold scales with both
+    pa.heavy_thr = std::max<uint32_t>(std::max<uint32_t>(32 >> R, ((uint32_t)hfac * avg) >> R), (uint32_t)((m >> R) / 175000));
+    if (pa.heavy_thr < 4) pa.heavy_thr = 4;
+    const size_t slots_max = m + (size_t)pl.nb * ((1u << R) - 1);   // padded entry slots (upper bound)
 
     if (int rc = cx.digits.reserve(m * 4)) return rc;
-    if (int rc = cx.vals.reserve(m * 4)) return rc;
+    if (int rc = cx.vals.reserve(slots_max * 4)) return rc;
     if (int rc = cx.cnt.reserve((size_t)pl.nb * 4)) return rc;
     if (int rc = cx.ord.reserve((size_t)pl.nb * 4)) return rc;
     for (int i = 0; i < 2; i++) {
@@ -350,60 +406,110 @@ int run_pass(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v, con
     }
     if (int rc = cx.start.reserve(((size_t)pl.nb + 2) * 4)) return rc;
     if (int rc = cx.buckets.reserve((size_t)pl.nb * PB)) return rc;
-    // heavy buckets: one thread per bucket is the efficient shape (≈0.31 product-times per entry
-    // per warp vs ≈1 for the block-cooperative path), so a bucket only counts as heavy when its
-    // serial chain would be a visible fraction (≈8 %) of the whole accumulation — the kernel lasts
-    // ≈ m/175k bucket-entry times — or when it exceeds 3× the mean occupancy, whichever is larger.
-    // Buckets are taken in decreasing-size order, so the long chains start first.
-    // Worst-case list sizes follow from Σ counts = m.
-    // (table mode: the buckets the top window also feeds hold up to ≈2.3× the mean, so the factor is 4 there)
-    const uint32_t avg = (uint32_t)(((tbl ? m : entries) + pl.nbw - 1) / pl.nbw);
-    const int hfac = tn.heavy_factor ? tn.heavy_factor : (tbl ? 4 : 3);
-    const uint32_t heavy_thr = std::max<uint32_t>(std::max<uint32_t>(32, (uint32_t)hfac * avg), (uint32_t)(m / 175000));
-    const size_t max_heavy = m / (heavy_thr + 1) + 1, max_tasks = m / HEAVY_CHUNK + max_heavy + 1;
+    const size_t m_acc = slots_max >> R;      // entries the XYZZ accumulation (and its heavy path) sees
+    const size_t max_heavy = m_acc / (pa.heavy_thr + 1) + 1, max_tasks = m_acc / HEAVY_CHUNK + max_heavy + 1;
     if (int rc = cx.hvy_hdr.reserve(16)) return rc;
     if (int rc = cx.hvy_buckets.reserve(max_heavy * 12)) return rc;
     if (int rc = cx.hvy_tasks.reserve(max_tasks * 8)) return rc;
     if (int rc = cx.hvy_partials.reserve(max_tasks * PB)) return rc;
-    uint32_t *vals = cx.vals.as<uint32_t>(), *ord = cx.ord.as<uint32_t>();
-    uint32_t *start = cx.start.as<uint32_t>();
     if (int rc = cx.tile_sums.reserve(((size_t)pl.nb / 2048 + 4) * 4)) return rc;
     if (int rc = cx.size_hist.reserve(2 * 4096 * 4)) return rc;
+    if (pl.glv)
+        if (int rc = cx.endo.reserve(n * (size_t)W * 4)) return rc;
+    if (R > 0) {
+        const size_t FB = (size_t)W * 4, s1 = (slots_max + 1) / 2;
+        const BaPlan bp = ba_plan(s1, cx.sm_count);
+        if (int rc = cx.ba_prefix.reserve(((size_t)bp.NT * bp.K + 4096) * FB)) return rc;
+        if (int rc = cx.ba_T.reserve(((size_t)bp.NT + 256) * FB)) return rc;
+        if (int rc = cx.ba_prefix2.reserve(((size_t)bp.NT + 256) * FB)) return rc;
+        if (int rc = cx.ba_U.reserve(((size_t)bp.NU + 64) * FB)) return rc;
+        if (int rc = cx.ba_pts[0].reserve(s1 * 2 * FB)) return rc;
+        if (R > 1)
+            if (int rc = cx.ba_pts[1].reserve((s1 + 1) / 2 * 2 * FB)) return rc;
+    }
+    if (pa.finish) {
+        uint32_t len = pl.nbw;
+        while (len > 2048 && (!tbl || len / 32 >= 4096)) len /= 32;
+        const size_t tstride = std::max<uint32_t>(1, len / 2);
+        for (int i = 0; i < 2; i++) {
+            if (int rc = cx.treeS[i].reserve((size_t)rwin * tstride * PB)) return rc;
+            if (int rc = cx.treeV[i].reserve((size_t)rwin * tstride * PB)) return rc;
+            if (int rc = cx.treeC[i].reserve((size_t)rwin * tstride * PB)) return rc;
+        }
+        if (int rc = cx.wsum.reserve((size_t)rwin * PB)) return rc;
+    }
+    pa.arena = cx.arena_epoch();
+    return 0;
+}
 
+// Stage 1 of a pass — the scalar side: canonical scalars → window digits, per-bucket histogram, scan → bucket
+// offsets, scatter of the point indices (a counting sort on the bucket id; zero digits are dropped), buckets in
+// decreasing-size order.  Does not read the bases, so it runs while they are still crossing PCIe.
+int pass_issue_prep(DeviceCtx &cx, const PassArgs &pa, cudaStream_t st, bool prof, int &evi) {
+    auto mark = [&]() { if (prof) cudaEventRecord(cx.ev[evi++], st); };
     mark();
-    // 1+2. canonical scalars → window digits, per-bucket histogram, scan → bucket offsets, scatter
-    //      of the point indices (a counting sort on the bucket id; zero digits are dropped)
-    launch_group_by_bucket(d_scalars, n, mont, pl.glv ? (pl.split ? 2 : 1) : 0, pl.c, pl.nwin, pl.nb, cx.digits.as<uint32_t>(), cx.cnt.as<uint32_t>(), start,
-                           cx.tile_sums.as<uint32_t>(), vals, st, tbl ? tbl->stride : 0);
+    launch_group_by_bucket(pa.d_scalars, pa.n, pa.mont, pa.glv, pa.c, pa.nwin, pa.nb, cx.digits.as<uint32_t>(), cx.cnt.as<uint32_t>(),
+                           cx.start.as<uint32_t>(), cx.tile_sums.as<uint32_t>(), cx.vals.as<uint32_t>(), st, pa.tbl_stride, pa.R);
     mark();
     mark();
-    // 3. buckets in decreasing-size order (sizes above 4095 all sort first)
-    launch_order_by_size(start, pl.nb, cx.size_hist.as<uint32_t>(), ord, st);
+    launch_order_by_size(cx.start.as<uint32_t>(), pa.nb, cx.size_hist.as<uint32_t>(), cx.ord.as<uint32_t>(), st);
     mark();
-    // 4. bucket accumulation
     CUDA_TRY(cudaMemsetAsync(cx.hvy_hdr.p, 0, 16, st));
-    if (bases_ready) CUDA_TRY(cudaStreamWaitEvent(st, bases_ready, 0));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// Stage 2 — everything that touches points: (GLV) β·x table, batched-affine pairing rounds, XYZZ bucket
+// accumulation with the heavy buckets on a side stream, and — when `finish` — bucket reduction and window combination.
+int pass_issue_main(DeviceCtx &cx, const PassArgs &pa, cudaStream_t st, bool prof, int &evi) {
+    const bool g2 = pa.group == B200MSM_G2;
+    const int W = g2 ? 24 : 12;
+    const bool tbl = pa.tbl_p != nullptr;
+    const int rwin = tbl ? 1 : pa.nwin;
+    auto mark = [&]() { if (prof) cudaEventRecord(cx.ev[evi++], st); };
+    uint32_t *vals = cx.vals.as<uint32_t>(), *ord = cx.ord.as<uint32_t>(), *start = cx.start.as<uint32_t>();
     const uint32_t *endo_x = nullptr;
     uint32_t n_pts = 0xffffffffu;
-    if (pl.glv) {  // β·x table for the endomorphism images (one product per base)
-        if (int rc = cx.endo.reserve(n * (size_t)W * 4)) return rc;
-        (g2 ? launch_endo_table_g2 : launch_endo_table_g1)(d_bases, n, cx.endo.as<uint32_t>(), st);
+    if (pa.glv) {  // β·x table for the endomorphism images (one product per base)
+        (g2 ? launch_endo_table_g2 : launch_endo_table_g1)(pa.d_bases, pa.n, cx.endo.as<uint32_t>(), st);
         endo_x = cx.endo.as<uint32_t>();
-        n_pts = (uint32_t)n;
+        n_pts = (uint32_t)pa.n;
     }
-    // heavy buckets run on a side stream next to the light kernel (disjoint outputs): each fills
-    // the SMs the other leaves idle at its tail
+    // 4a. batched-affine pairing rounds (batch_affine.cuh): the (padded) entry array is halved R times by affine
+    //     additions that share one inversion per ≈10^5 pairs; what is left is accumulated in XYZZ form below
+    const uint32_t *acc_pts = pa.d_bases, *acc_vals = vals;
+    if (pa.R > 0) {
+        const size_t entries = pa.glv ? 2 * pa.n : pa.n, m = entries * (size_t)pa.nwin;
+        size_t s_out = (m + (size_t)pa.nb * ((1u << pa.R) - 1) + 1) / 2;
+        const uint32_t *src = pa.d_bases;
+        for (int r = 0; r < pa.R; r++) {
+            const BaPlan bp = ba_plan(s_out, cx.sm_count);
+            uint32_t *out = cx.ba_pts[r & 1].as<uint32_t>();
+            (g2 ? launch_ba_round_g2 : launch_ba_round_g1)(r == 0, src, vals, endo_x, n_pts, start + pa.nb, r, bp, cx.ba_prefix.as<uint32_t>(),
+                                                           cx.ba_T.as<uint32_t>(), cx.ba_prefix2.as<uint32_t>(), cx.ba_U.as<uint32_t>(), out, st);
+            src = out;
+            s_out = (s_out + 1) / 2;
+        }
+        acc_pts = src;
+        acc_vals = nullptr;
+    }
+    // 4b. heavy buckets run on a side stream next to the light kernel (disjoint outputs): each fills
+    //     the SMs the other leaves idle at its tail
     CUDA_TRY(cudaEventRecord(cx.ev_fork, st));
     CUDA_TRY(cudaStreamWaitEvent(cx.aux_stream, cx.ev_fork, 0));
-    (g2 ? launch_heavy_g2 : launch_heavy_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, endo_x, n_pts, cx.hvy_hdr.p,
-                                             cx.hvy_buckets.p, cx.hvy_tasks.p, cx.hvy_partials.as<uint32_t>(), po.into ? 1 : 0,
-                                             cx.buckets.as<uint32_t>(), cx.sm_count * 4, cx.aux_stream);
+    (g2 ? launch_heavy_g2 : launch_heavy_g1)(acc_pts, acc_vals, start, ord, pa.nb, pa.heavy_thr, endo_x, n_pts, cx.hvy_hdr.p,
+                                             cx.hvy_buckets.p, cx.hvy_tasks.p, cx.hvy_partials.as<uint32_t>(), pa.into,
+                                             cx.buckets.as<uint32_t>(), cx.sm_count * 4, cx.aux_stream, pa.R);
     CUDA_TRY(cudaEventRecord(cx.ev_join, cx.aux_stream));
-    (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(d_bases, vals, start, ord, pl.nb, heavy_thr, endo_x, n_pts, po.into ? 1 : 0,
-                                                       cx.buckets.as<uint32_t>(), st);
+    if (pa.R > 0)
+        (g2 ? launch_accumulate_direct_g2 : launch_accumulate_direct_g1)(acc_pts, start, ord, pa.nb, pa.heavy_thr, pa.R, pa.into,
+                                                                         cx.buckets.as<uint32_t>(), st);
+    else
+        (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(pa.d_bases, vals, start, ord, pa.nb, pa.heavy_thr, endo_x, n_pts, pa.into,
+                                                           cx.buckets.as<uint32_t>(), st);
     CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_join, 0));
     mark();
-    if (!po.finish) {
+    if (!pa.finish) {
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
@@ -419,7 +525,7 @@ int run_pass(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v, con
     }
     const uint32_t *X = cx.buckets.as<uint32_t>();
     const uint32_t *Cin = nullptr;
-    uint32_t len = pl.nbw;
+    uint32_t len = pa.nbw;
     int log2M = 0, pp = 0;
     // (a single window — table mode — goes to the tree as soon as a level would leave fewer than 4096 chains)
     constexpr int fan_log = 5;                // fan-in 32: 16 and 8 measured equal or slower (profiles/r01_experiments.md)
@@ -437,12 +543,6 @@ int run_pass(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v, con
     int logS = 0;
     while ((1u << logS) < S) logS++;
     const size_t tstride = std::max<uint32_t>(1, S / 2);  // points per window in every tree array
-    for (int i = 0; i < 2; i++) {
-        if (int rc = cx.treeS[i].reserve((size_t)rwin * tstride * PB)) return rc;
-        if (int rc = cx.treeV[i].reserve((size_t)rwin * tstride * PB)) return rc;
-        if (int rc = cx.treeC[i].reserve((size_t)rwin * tstride * PB)) return rc;
-    }
-    if (int rc = cx.wsum.reserve((size_t)rwin * PB)) return rc;
     const uint32_t *Sin = X, *Ccur = Cin;
     size_t sin_stride = S, cin_stride = S;
     int cur = 0;
@@ -458,14 +558,111 @@ int run_pass(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v, con
     mark();
     // 6. window values and Horner over the windows → one Jacobian point
     (g2 ? launch_combine_g2 : launch_combine_g1)(Sin, cx.treeV[cur].as<uint32_t>(), Cin ? Ccur : nullptr, tstride, logS, log2M,
-                                                 rwin, pl.c, pl.split ? 1 : 0, cx.wsum.as<uint32_t>(), d_out, st);
+                                                 rwin, pa.c, pa.glv == 2 ? 1 : 0, cx.wsum.as<uint32_t>(), pa.d_out, st);
     mark();
     if (st != caller_st) {
         CUDA_TRY(cudaEventRecord(cx.ev_tail_join, st));
         CUDA_TRY(cudaStreamWaitEvent(caller_st, cx.ev_tail_join, 0));
     }
     CUDA_TRY(cudaGetLastError());
-    cx.phase_pending = prof;  // elapsed times are read lazily by b200msm_last_phase_ms (no sync here)
+    return 0;
+}
+
+// A pass seen for the second time with the same arguments (a prover repeats its sizes; every slice
+// of a streamed MSM; every step of a benchmark) is captured into two CUDA graphs — scalar side,
+// point side — and replayed from then on: two launches instead of ≈45, which is what keeps eight
+// host threads driving eight GPUs from one process off the driver's locks.  The wait for the bases'
+// upload stays between the two as an ordinary stream wait.
+int capture_stage(DeviceCtx &cx, const PassArgs &pa, cudaStream_t st, bool main_stage, cudaGraphExec_t *exec, unsigned long long *launches) {
+    (void)st;
+    const unsigned long long l0 = t_own_launches;
+    CUDA_TRY(cudaStreamBeginCapture(cx.cap_stream, cudaStreamCaptureModeThreadLocal));
+    int evi = 0;
+    int rc = main_stage ? pass_issue_main(cx, pa, cx.cap_stream, false, evi) : pass_issue_prep(cx, pa, cx.cap_stream, false, evi);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(cx.cap_stream, &g);
+    *launches = t_own_launches - l0;
+    __atomic_fetch_sub(&g_own_launches, *launches, __ATOMIC_RELAXED);    // counted when the graph is launched, not when it is recorded
+    if (rc) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        return rc;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B200MSM_ECUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    }
+    e = cudaGraphInstantiate(exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B200MSM_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+// The pipeline on one device. Inputs already in device memory; d_out receives 3 field elements.
+// Must be called with ctx.mu held and ctx.dev current. Asynchronous on `st`.
+// `bases_ready` (optional): an event after which d_bases is valid — the scalar-side phases
+// (digits, sort, bucket offsets) do not read the bases, so they overlap the bases' H2D copy.
+int run_pass(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v, const void *d_scalars_v, size_t n, int mont, void *d_out_v,
+              cudaStream_t st, cudaEvent_t bases_ready = nullptr, const TableRef *tbl = nullptr, const PassOpts &po = PassOpts()) {
+    if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "group must be B200MSM_G1 or B200MSM_G2");
+    const int W = group == B200MSM_G2 ? 24 : 12;
+    if (n == 0 && !po.plan) {
+        CUDA_TRY(cudaMemsetAsync(d_out_v, 0, 3 * W * 4, st));
+        return 0;
+    }
+    PassArgs pa;
+    if (int rc = pass_prepare(group, cx, tn, d_bases_v, d_scalars_v, n, mont, d_out_v, tbl, po, pa)) return rc;
+    const bool prof = tn.profiling;
+    int evi = 0;
+    PassGraph *pg = nullptr;
+    if (tn.graphs && !prof) {
+        for (auto &g : cx.graphs)
+            if (same_pass(g.key, pa)) { pg = &g; break; }
+        if (!pg) {
+            // first sight: remember the arguments and run directly; second sight: record
+            bool seen = false;
+            for (auto &k : cx.seen)
+                if (same_pass(k, pa)) { seen = true; break; }
+            if (!seen) {
+                if (cx.seen.size() >= 64) cx.seen.erase(cx.seen.begin());
+                cx.seen.push_back(pa);
+            } else {
+                if (cx.graphs.size() >= 48) {           // evict the least recently used
+                    size_t lru = 0;
+                    for (size_t i = 1; i < cx.graphs.size(); i++)
+                        if (cx.graphs[i].last_use < cx.graphs[lru].last_use) lru = i;
+                    cudaGraphExecDestroy(cx.graphs[lru].prep);
+                    cudaGraphExecDestroy(cx.graphs[lru].main);
+                    cx.graphs.erase(cx.graphs.begin() + lru);
+                }
+                PassGraph ng;
+                ng.key = pa;
+                memcpy(ng.plan, cx.last_plan, sizeof ng.plan);
+                if (capture_stage(cx, pa, st, false, &ng.prep, &ng.launches_prep) == 0) {
+                    if (capture_stage(cx, pa, st, true, &ng.main, &ng.launches_main) == 0) {
+                        cx.graphs.push_back(ng);
+                        pg = &cx.graphs.back();
+                    } else cudaGraphExecDestroy(ng.prep);
+                }
+                // (a failed capture falls back to direct issue below; the error text stays in last_error)
+            }
+        }
+    }
+    if (pg) {
+        pg->last_use = ++cx.graph_clock;
+        CUDA_TRY(cudaGraphLaunch(pg->prep, st));
+        if (bases_ready) CUDA_TRY(cudaStreamWaitEvent(st, bases_ready, 0));
+        CUDA_TRY(cudaGraphLaunch(pg->main, st));
+        __atomic_fetch_add(&g_own_launches, pg->launches_prep + pg->launches_main, __ATOMIC_RELAXED);
+        return 0;
+    }
+    if (int rc = pass_issue_prep(cx, pa, st, prof, evi)) return rc;
+    if (bases_ready) CUDA_TRY(cudaStreamWaitEvent(st, bases_ready, 0));
+    if (int rc = pass_issue_main(cx, pa, st, prof, evi)) return rc;
+    cx.phase_pending = prof && pa.finish;  // elapsed times are read lazily by b200msm_last_phase_ms (no sync here)
     return 0;
 }
 
@@ -475,8 +672,9 @@ size_t pass_scratch_bytes(size_t n, bool g2, int c_override, bool table = false)
     c = std::max(2, std::min(c, 22));
     size_t nwin = (256 + c - 1) / c, nb = nwin << (c - 1), m = n * nwin;  // the GLV plan needs about the same
     size_t PB = g2 ? 384 : 192;
-    if (table) return m * 8 + (nb / nwin) * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + (64u << 20);
-    return m * 8 + nb * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + n * (PB / 4) + (64u << 20);
+    const size_t ba = m * (PB * 3 / 8) + nb * 16;   // batched-affine rounds: prefix products + the first round's output (upper bound)
+    if (table) return m * 8 + (nb / nwin) * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + ba + (64u << 20);
+    return m * 8 + nb * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + n * (PB / 4) + ba + (64u << 20);
 }
 
 // The whole MSM on one device: one pass when it fits, otherwise the chunking the reference left
@@ -1184,6 +1382,15 @@ int b200msm_set_glv(int mode) {
     tun_update([&](Tun &t) { t.glv_mode = mode; });
     return 0;
 }
+int b200msm_set_batch_affine(int rounds) {
+    if (rounds < -1 || rounds > 3) return fail(B200MSM_EINVAL, "batched-affine rounds must be -1 (auto), 0 (off) or 1..3");
+    tun_update([&](Tun &t) { t.batch_affine = rounds; });
+    return 0;
+}
+int b200msm_set_graphs(int on) {
+    tun_update([&](Tun &t) { t.graphs = on != 0; }, false);
+    return 0;
+}
 int b200msm_set_max_chunk(size_t max_points_per_pass) {
     tun_update([&](Tun &t) { t.max_chunk_override = max_points_per_pass; });
     return 0;
@@ -1296,7 +1503,8 @@ int b200msm_dbg_field_op(int is_fp2, int op, const uint64_t *a, const uint64_t *
     CUDA_TRY(cudaMalloc(&dout, n * EB));
     CUDA_TRY(cudaMemcpy(da, a, n * EB, cudaMemcpyHostToDevice));
     if (b) CUDA_TRY(cudaMemcpy(db, b, n * EB, cudaMemcpyHostToDevice));
-    launch_dbg_field_op(is_fp2, op, da, db, dout, n);
+    if (op == 6) launch_dbg_inv_sg(is_fp2, da, dout, n, 0);
+    else launch_dbg_field_op(is_fp2, op, da, db, dout, n);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(out, dout, n * EB, cudaMemcpyDeviceToHost));
     cudaFree(da);

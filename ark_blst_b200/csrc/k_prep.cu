@@ -109,12 +109,12 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
     return base + x - v;
 }
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_tiles(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n, uint32_t *__restrict__ tile_sums) {
+k_scan_tiles(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n, uint32_t *__restrict__ tile_sums, uint32_t pad_mask) {
     size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS], sum = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-        v[k] = base + k < n ? in[base + k] : 0;
+        v[k] = base + k < n ? (in[base + k] + pad_mask) & ~pad_mask : 0;   // bucket sizes rounded up to the padding unit
         sum += v[k];
     }
     uint32_t total;
@@ -207,12 +207,14 @@ k_size_scatter(const uint32_t *__restrict__ start, uint32_t nb, uint32_t *__rest
 
 void launch_group_by_bucket(const uint32_t *scalars, size_t n, int mont, int glv, int c, int nwin, uint32_t nb, uint32_t *dig,
                             uint32_t *count, uint32_t *start, uint32_t *tile_sums, uint32_t *vals, cudaStream_t st,
-                            size_t tbl_stride) {
+                            size_t tbl_stride, int pad_log) {
     for (int k = 0; k < 7; k++) count_launch();
+    const uint32_t pad_mask = (1u << pad_log) - 1;
+    if (pad_log) cudaMemsetAsync(vals, 0xff, ((glv ? 2 * n : n) * (size_t)nwin + (size_t)nb * pad_mask) * 4, st);
     cudaMemsetAsync(count, 0, (size_t)nb * 4, st);
     k_hist<<<blocks_for(n, 256), 256, 0, st>>>(scalars, n, mont, glv, c, nwin, tbl_stride ? 1 : 0, dig, count);
     size_t ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(count, start, nb, tile_sums);
+    k_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(count, start, nb, tile_sums, pad_mask);
     k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, ntiles, tile_sums + ntiles);
     k_scan_add<<<blocks_for(nb, 256), 256, 0, st>>>(start, nb, tile_sums, tile_sums + ntiles);
     cudaMemsetAsync(count, 0, (size_t)nb * 4, st);   // reused as the scatter cursors

@@ -15,9 +15,11 @@ void launch_digits_dbg(const uint32_t *scalars, size_t n, int mont, int c, int n
 // unsigned and spread over the last two windows (c | 128, nwin = 128/c + 1; see k_hist); dig: entries·nwin u32, count: nb u32, start: nb+2 u32, tile_sums: nb/2048+2 u32, vals: ≥ n·nwin u32
 // tbl_stride > 0 (fixed-base window table, `tbl_stride` points per window): all windows share one bucket set — nb = 2^(c−1),
 // entries are grouped by the digit alone and carry the table index w·tbl_stride + i (must stay below 2^31)
+// pad_log > 0 (batched-affine rounds follow): every bucket's segment is padded to a multiple of 2^pad_log entries and
+// the padding slots of vals hold 0xffffffff (vals must then hold n·nwin + nb·(2^pad_log − 1) entries)
 void launch_group_by_bucket(const uint32_t *scalars, size_t n, int mont, int glv, int c, int nwin, uint32_t nb, uint32_t *dig,
                             uint32_t *count, uint32_t *start, uint32_t *tile_sums, uint32_t *vals, cudaStream_t st,
-                            size_t tbl_stride = 0);
+                            size_t tbl_stride = 0, int pad_log = 0);
 // bucket ids in decreasing-size order (counting sort on the clamped size); hist: 8192 u32 scratch
 void launch_order_by_size(const uint32_t *start, uint32_t nb, uint32_t *hist, uint32_t *order, cudaStream_t st);
 // k_accumulate_g{1,2}.cu
@@ -35,10 +37,31 @@ void launch_endo_table_g2(const uint32_t *bases, size_t n, uint32_t *endo_x, cud
 // plan + block tasks + per-bucket fold for buckets above heavy_thr; hdr must be zeroed (8 bytes)
 void launch_heavy_g1(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
                      uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, void *hdr, void *hb, void *tasks,
-                     uint32_t *partials, int into, uint32_t *buckets, int grid, cudaStream_t st);
+                     uint32_t *partials, int into, uint32_t *buckets, int grid, cudaStream_t st, int shift = 0);
 void launch_heavy_g2(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
                      uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, void *hdr, void *hb, void *tasks,
-                     uint32_t *partials, int into, uint32_t *buckets, int grid, cudaStream_t st);
+                     uint32_t *partials, int into, uint32_t *buckets, int grid, cudaStream_t st, int shift = 0);
+// (vals == nullptr with shift = R: direct mode over the array the batched-affine rounds left, see k_batch_g{1,2}.cu)
+
+// k_batch_g{1,2}.cu — batched-affine pairing rounds (batch_affine.cuh).  One round halves the (padded) entry array:
+// first = 1 reads entries through vals from the bases (sign / GLV image applied), else from `src` (the previous
+// round's output).  total_ptr → the scan's grand total (slots of the entry array); round = 0-based; s_out_max bounds
+// the output slots on the host.  Scratch: prefix ≥ NT·K elements, T and prefix2 ≥ NT, U ≥ NU (sizes from ba_plan).
+struct BaPlan { uint32_t NT, K, NU, K2; };
+BaPlan ba_plan(size_t s_out_max, int sm_count);
+void launch_ba_round_g1(int first, const uint32_t *src, const uint32_t *vals, const uint32_t *endo_x, uint32_t n_pts,
+                        const uint32_t *total_ptr, int round, const BaPlan &bp, uint32_t *prefix, uint32_t *T, uint32_t *prefix2,
+                        uint32_t *U, uint32_t *out, cudaStream_t st);
+void launch_ba_round_g2(int first, const uint32_t *src, const uint32_t *vals, const uint32_t *endo_x, uint32_t n_pts,
+                        const uint32_t *total_ptr, int round, const BaPlan &bp, uint32_t *prefix, uint32_t *T, uint32_t *prefix2,
+                        uint32_t *U, uint32_t *out, cudaStream_t st);
+void launch_accumulate_direct_g1(const uint32_t *pts, const uint32_t *start, const uint32_t *order, uint32_t nb, uint32_t heavy_thr,
+                                 int shift, int into, uint32_t *buckets, cudaStream_t st);
+void launch_accumulate_direct_g2(const uint32_t *pts, const uint32_t *start, const uint32_t *order, uint32_t nb, uint32_t heavy_thr,
+                                 int shift, int into, uint32_t *buckets, cudaStream_t st);
+// unit hooks: out[i] = 1/in[i] by divsteps (Montgomery form in and out); one standalone round over explicit affine pairs
+void launch_dbg_inv_sg(int is_fp2, const uint32_t *in, uint32_t *out, size_t n, cudaStream_t st);
+
 // jac_out[i] = 2^c · prev[i] (affine in, Jacobian out): one window step of the table build
 void launch_table_shift_g1(const uint32_t *prev, size_t n, int c, uint32_t *jac_out, cudaStream_t st);
 void launch_table_shift_g2(const uint32_t *prev, size_t n, int c, uint32_t *jac_out, cudaStream_t st);
@@ -81,7 +104,11 @@ void launch_dbg_point_op_g2(int op, const uint32_t *acc, const uint32_t *q, uint
 
 // number of this library's own kernel launches since load (bench.py reports the per-step count)
 extern unsigned long long g_own_launches;
-inline void count_launch() { __atomic_fetch_add(&g_own_launches, 1ull, __ATOMIC_RELAXED); }
+extern thread_local unsigned long long t_own_launches;   // the calling thread's share (graph recording subtracts it again)
+inline void count_launch() {
+    __atomic_fetch_add(&g_own_launches, 1ull, __ATOMIC_RELAXED);
+    t_own_launches++;
+}
 
 inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 

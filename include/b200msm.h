@@ -138,6 +138,16 @@ int b200msm_set_window_bits(int c);
  * number of bucket additions. -1 = automatic (time model; the default: on for n ≤ 2^22), 0 = never,
  * 1 = always. Results are the same group elements either way. */
 int b200msm_set_glv(int mode);
+/* Batched-affine pairing rounds in front of the XYZZ bucket accumulation: the sorted entry array is halved
+ * `rounds` times by affine additions that share one field inversion per ≈10^5 pairs (6 products per addition
+ * instead of 10 for G1, 17 instead of 28 for G2); what is left of every bucket is accumulated in XYZZ form.
+ * -1 = automatic (the default: 2 rounds from ≈40 entries per bucket, 1 from ≈14, else none), 0 = never, 1..3 forced.
+ * Results are the same group elements either way. */
+int b200msm_set_batch_affine(int rounds);
+/* A pass called a second time with the same arguments (sizes, plan, device pointers) is recorded as two CUDA
+ * graphs and replayed from then on: 2 launches instead of ≈45 per pass.  1 = on (default), 0 = always issue
+ * kernel by kernel.  Never used while b200msm_set_profiling(1). */
+int b200msm_set_graphs(int on);
 /* Page-lock a caller-owned host buffer (a long-lived scalar or base array) so that the host-buffer
  * entry points copy from it asynchronously at full PCIe rate: ordinary pageable memory is staged
  * by the driver at about a fifth of that and blocks the calling thread (G1 2^20 one-shot: 8.3 ms
@@ -188,7 +198,8 @@ int b200msm_synth_scalars_device(uint64_t seed, size_t n, int montgomery, void *
 int b200msm_imad_peak(double out[3]);
 
 /* ---- unit hooks used by the parity tests (element-wise, device-side, host buffers) ---- */
-/* op: 0 mul, 1 add, 2 sub, 3 sqr(b ignored), 4 neg(b ignored), 5 inv(b ignored).
+/* op: 0 mul, 1 add, 2 sub, 3 sqr(b ignored), 4 neg(b ignored), 5 inv(b ignored; Fermat power),
+ * 6 inv by divsteps (b ignored; csrc/modinv.cuh — the inversion the batched-affine rounds share).
  * a, b, out: n elements of 6 (Fp) or 12 (Fp2) u64 each. */
 int b200msm_dbg_field_op(int fp2, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
 /* op: 0 madd (acc XYZZ + affine), 1 add (XYZZ + XYZZ), 2 dbl (XYZZ); results as XYZZ→Jacobian.

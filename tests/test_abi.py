@@ -165,3 +165,27 @@ def test_bench_counts_the_nonzero_digits_of_witness_like_scalars(cref):
     c, W, _, _ = bench.work_model(1 << 22, False)
     assert bench.count_nonzero_booth_digits(s, c) < 0.45 * bench.count_nonzero_booth_digits(uni, c)
     assert bench.work_model_counted(bench.count_nonzero_booth_digits(s, c), 1 << 22, False) < bench.work_model(1 << 22, False)[2]
+
+
+def test_divsteps_inversion_on_the_host(tmp_path):
+    """csrc/modinv.cuh is plain integer code: compiled with g++ here and checked against Python's pow(x, −1, p)
+    (the device runs the same source; tests/test_gpu_batch_affine.py checks it there)"""
+    import random
+
+    from oracle import bls12381 as o
+
+    src = tmp_path / "w.cpp"
+    src.write_text('#include "%s"\nextern "C" void mi_inv(const uint32_t *a, uint32_t *out, int n) {'
+                   ' for (int i = 0; i < n; i++) b200msm::mi_inverse_u32(out + 12 * i, a + 12 * i); }\n'
+                   % os.path.join(ROOT, "ark_blst_b200", "csrc", "modinv.cuh"))
+    so = str(tmp_path / "libmi.so")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", so, str(src)], check=True)
+    L = ctypes.CDLL(so)
+    rng = random.Random(1)
+    p = o.P
+    vals = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, 1 << 380, 3, 1 << 30, (1 << 30) - 1, 1 << 60] + [rng.randrange(p) for _ in range(5000)]
+    a = np.array([[(v >> (32 * i)) & 0xFFFFFFFF for i in range(12)] for v in vals], dtype=np.uint32)
+    out = np.zeros_like(a)
+    L.mi_inv(a.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), len(vals))
+    for v, row in zip(vals, out):
+        assert sum(int(x) << (32 * i) for i, x in enumerate(row)) == (pow(v, -1, p) if v else 0)

@@ -1,0 +1,163 @@
+"""Batched-affine pairing rounds (csrc/batch_affine.cuh) and CUDA-graph replay (run_pass): every forced
+configuration must give the same group element as the oracle, incl. the exceptional cases INSIDE a
+batch — P + P (doubling), P + (−P) (cancellation), identity bases, padding slots."""
+import random
+
+import numpy as np
+import pytest
+
+from helpers import curve, jac_to_point, points_to_limbs, rand_fp2_limbs, rand_fp_limbs, scalars_to_limbs
+from oracle import bls12381 as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _grp(eng, g2):
+    return eng.G2Projective if g2 else eng.G1Projective
+
+
+@pytest.fixture
+def knobs(eng):
+    L = eng._lib.lib
+    yield L
+    L.b200msm_set_batch_affine(-1)
+    L.b200msm_set_graphs(1)
+    L.b200msm_set_glv(-1)
+    L.b200msm_set_window_bits(0)
+    L.b200msm_set_stream_slices(8, 0)
+    L.b200msm_set_max_chunk(0)
+    L.b200msm_set_heavy_factor(0)
+
+
+def test_divsteps_inverse_matches_bigint(eng):
+    """op 6 of the field hook = csrc/modinv.cuh on the device, Fp and Fp2, incl. 1, p−1 and small values"""
+    u = eng._lib.u64p
+    rng = random.Random(61)
+    vals = [1, 2, o.P - 1, o.P - 2, (o.P - 1) // 2, 3, 1 << 30, (1 << 30) - 1, 1 << 64, o.MONT_RINV] + [rng.randrange(1, o.P) for _ in range(1000)]
+    a = np.array([o.FpOps.to_limbs(v) for v in vals], dtype=np.uint64)
+    out = np.zeros_like(a)
+    assert eng._lib.lib.b200msm_dbg_field_op(0, 6, a.ctypes.data_as(u), a.ctypes.data_as(u), out.ctypes.data_as(u), a.shape[0]) == 0
+    assert np.array_equal(out, np.array([o.FpOps.to_limbs(o.FpOps.inv(v)) for v in vals], dtype=np.uint64))
+    av, a2 = rand_fp2_limbs(rng, 300, edge=False)
+    av[:3] = [(1, 0), (0, 1), (o.P - 1, o.P - 1)]
+    a2 = np.array([o.Fp2Ops.to_limbs(v) for v in av], dtype=np.uint64)
+    out2 = np.zeros_like(a2)
+    assert eng._lib.lib.b200msm_dbg_field_op(1, 6, a2.ctypes.data_as(u), a2.ctypes.data_as(u), out2.ctypes.data_as(u), a2.shape[0]) == 0
+    assert np.array_equal(out2, np.array([o.Fp2Ops.to_limbs(o.Fp2Ops.inv(v)) for v in av], dtype=np.uint64))
+
+
+@pytest.mark.parametrize("g2", [0, 1])
+@pytest.mark.parametrize("rounds", [1, 2, 3])
+def test_exceptional_cases_inside_a_batch(eng, knobs, g2, rounds):
+    """few distinct points and tiny scalars: every bucket is full of repeated points, opposite points and
+    identities, so the rounds hit doubling, cancellation, copies and empty slots at every level"""
+    C = curve(g2)
+    rng = random.Random(500 + 10 * g2 + rounds)
+    base = [C.mul(C.gen, rng.randrange(1, o.R_ORDER)) for _ in range(3)]
+    pool = base + [C.neg(p) for p in base] + [None]
+    assert knobs.b200msm_set_batch_affine(rounds) == 0
+    for n, smax in ((1, 3), (2, 3), (5, 2), (64, 4), (257, 3), (700, 6)):
+        pts = [pool[rng.randrange(len(pool))] for _ in range(n)]
+        sc = [rng.randrange(smax) for _ in range(n)]
+        exp = C.msm_naive(pts, sc)
+        for glv in (0, 1):
+            assert knobs.b200msm_set_glv(glv) == 0
+            got = _grp(eng, g2).msm(points_to_limbs(C, pts), scalars_to_limbs(sc, True))
+            assert C.eq(jac_to_point(C, got), exp), (n, smax, glv)
+    # the same point n times with the same scalar: log2(n) levels of pure doublings
+    P = base[0]
+    for n in (2, 4, 7, 8, 33):
+        exp = C.mul(P, 5 * n % o.R_ORDER)
+        got = _grp(eng, g2).msm(points_to_limbs(C, [P] * n), scalars_to_limbs([5] * n, True))
+        assert C.eq(jac_to_point(C, got), exp), n
+
+
+@pytest.mark.parametrize("g2,n", [(0, 3000), (0, (1 << 15) + 11), (1, 2500)])
+@pytest.mark.parametrize("rounds", [0, 1, 2, 3])
+def test_rounds_vs_c_oracle(eng, cref, knobs, g2, n, rounds):
+    bases = cref.synth_bases(g2, 3100 + n, n)
+    sm = cref.synth_scalars(3200 + n, n, True)
+    sc = cref.synth_scalars(3200 + n, n, False)
+    exp = cref.msm(g2, bases, sc, 0)
+    assert knobs.b200msm_set_batch_affine(rounds) == 0
+    for c, glv in ((0, -1), (8, 0), (11, 1), (5, 0)):   # small widths make full buckets, where the rounds do real additions
+        assert knobs.b200msm_set_window_bits(c) == 0 and knobs.b200msm_set_glv(glv) == 0
+        assert cref.affine_equal(g2, _grp(eng, g2).msm(bases, sm), exp), (c, glv)
+        assert cref.affine_equal(g2, _grp(eng, g2).msm_bigint(bases, sc), exp), (c, glv)
+
+
+@pytest.mark.parametrize("rounds", [1, 2])
+def test_rounds_with_every_host_path(eng, cref, knobs, rounds):
+    """streamed slices (accumulate INTO shared buckets), chunked passes, resident bases, fixed-base table,
+    witness-like scalars (one huge bucket: the heavy path reads what the rounds left)"""
+    g2, n = 0, 40000
+    bases = cref.synth_bases(g2, 4100, n)
+    sc = cref.synth_scalars(4200, n, False)
+    sc[: n // 2] = 0
+    sc[n // 2: n // 2 + n // 4, 0] = 1
+    sc[n // 2: n // 2 + n // 4, 1:] = 0
+    sm = np.array([o.scalar_to_limbs(o.limbs_to_int(r), True) for r in sc.tolist()], dtype=np.uint64)
+    exp = cref.msm(g2, bases, sc, 0)
+    assert knobs.b200msm_set_batch_affine(rounds) == 0
+    assert knobs.b200msm_set_window_bits(9) == 0
+    G = eng.G1Projective
+    assert cref.affine_equal(g2, G.msm(bases, sm), exp)
+    assert knobs.b200msm_set_stream_slices(8, 1024) == 0          # streamed
+    assert cref.affine_equal(g2, G.msm(bases, sm), exp)
+    assert knobs.b200msm_set_stream_slices(1, 0) == 0
+    assert knobs.b200msm_set_max_chunk(7000) == 0                 # chunked
+    assert cref.affine_equal(g2, G.msm(bases, sm), exp)
+    assert knobs.b200msm_set_max_chunk(0) == 0
+    assert knobs.b200msm_set_heavy_factor(1) == 0                 # many heavy buckets
+    assert cref.affine_equal(g2, G.msm(bases, sm), exp)
+    assert knobs.b200msm_set_heavy_factor(0) == 0
+    assert knobs.b200msm_set_window_bits(0) == 0
+    rb = eng.ResidentBases(G, bases)
+    try:
+        assert cref.affine_equal(g2, rb.msm(sm), exp)
+        rb.precompute(10)
+        assert cref.affine_equal(g2, rb.msm(sm), exp)
+        assert cref.affine_equal(g2, rb.msm(sm[:12345]), cref.msm(g2, bases[:12345], sc[:12345], 0))
+    finally:
+        rb.close()
+
+
+@pytest.mark.parametrize("g2", [0, 1])
+def test_graph_replay_is_bit_exact(eng, cref, knobs, g2):
+    """the same call four times: issued directly, recorded as CUDA graphs on the second sight, replayed after;
+    then with graphs off; then new scalars in the same buffers (the graphs hold pointers, not data)"""
+    import torch
+
+    n = 20000
+    aw, jw = (24, 36) if g2 else (12, 18)
+    G = eng.G2 if g2 else eng.G1
+    bases = torch.empty((n, aw), dtype=torch.int64, device="cuda")
+    scalars = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    out = torch.zeros(jw, dtype=torch.int64, device="cuda")
+    eng.synth_bases_device(G, 5100, n, bases.data_ptr())
+    st = torch.cuda.Stream()
+    for seed in (5200, 5201):
+        eng.synth_scalars_device(seed, n, True, scalars.data_ptr())
+        torch.cuda.synchronize()
+        exp = cref.msm_by_dlog(g2, 5100, cref.synth_scalars(seed, n, False))
+        for rep in range(4):
+            out.zero_()
+            eng.run_device(G, bases.data_ptr(), scalars.data_ptr(), n, True, out.data_ptr(), st.cuda_stream)
+            st.synchronize()
+            assert cref.affine_equal(g2, out.cpu().numpy().view(np.uint64), exp), (seed, rep)
+    launches0 = knobs.b200msm_launch_count()
+    eng.run_device(G, bases.data_ptr(), scalars.data_ptr(), n, True, out.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    replay = knobs.b200msm_launch_count() - launches0
+    assert knobs.b200msm_set_graphs(0) == 0
+    launches0 = knobs.b200msm_launch_count()
+    eng.run_device(G, bases.data_ptr(), scalars.data_ptr(), n, True, out.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    assert knobs.b200msm_launch_count() - launches0 == replay > 20      # the graph runs the same kernels, and says so
+    assert cref.affine_equal(g2, out.cpu().numpy().view(np.uint64), exp)
+    # the legacy default stream cannot be captured: the library records on a stream of its own
+    assert knobs.b200msm_set_graphs(1) == 0
+    for rep in range(3):
+        eng.run_device(G, bases.data_ptr(), scalars.data_ptr(), n, True, out.data_ptr(), 0)
+        torch.cuda.synchronize()
+        assert cref.affine_equal(g2, out.cpu().numpy().view(np.uint64), exp)

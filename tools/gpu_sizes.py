@@ -12,6 +12,7 @@ L.b200msm_set_profiling(1)
 import os
 if os.environ.get("GLV"): L.b200msm_set_glv(int(os.environ["GLV"]))
 if os.environ.get("WBITS"): L.b200msm_set_window_bits(int(os.environ["WBITS"]))
+if os.environ.get("BA"): L.b200msm_set_batch_affine(int(os.environ["BA"]))
 peak = eng.imad_peak()["imad_per_s"]
 sys.path.insert(0, ".")
 from bench import work_model, FPMUL_IMAD
