@@ -368,7 +368,7 @@ int pass_prepare(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v,
         pl.glv = pl.split = false;
         pl.nbw = 1u << (pl.c - 1);
         pl.nb = pl.nbw;                       // one bucket set shared by all windows
-    } else auto_plan(n, g2, tn.glv_mode, tn.window_override, pl);
+    } else auto_plan(n, g2, tn.glv_mode, tn.window_override, pl, tn.batch_affine);
     if (tbl) { pa.d_bases = (const uint32_t *)tbl->p; pa.tbl_p = tbl->p; pa.tbl_stride = tbl->stride; }
     pa.c = pl.c; pa.nwin = pl.nwin; pa.glv = pl.glv ? (pl.split ? 2 : 1) : 0; pa.nbw = pl.nbw; pa.nb = pl.nb;
     const int rwin = tbl ? 1 : pl.nwin;       // windows the reduction sees
@@ -386,7 +386,7 @@ int pass_prepare(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v,
     // batched-affine pairing rounds: they pay when a bucket holds enough entries for the pairs to be real additions
     // (padding to 2^R entries per bucket is wasted slots) — measured crossover, see profiles/r02_experiments.md
     int R = tn.batch_affine;
-    if (R < 0) R = avg >= 40 ? 2 : (avg >= 14 ? 1 : 0);
+    if (R < 0) R = ba_rounds_for((double)avg);
     if (n == 0) R = 0;
     pa.R = R;
     const int hfac = tn.heavy_factor ? tn.heavy_factor : (tbl ? 4 : 3);
@@ -706,7 +706,7 @@ int run_group(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases, cons
         if (tn.max_chunk_override) return cn > tn.max_chunk_override;
         if (tbl) return cn * tbl->nwin >= 0xfff00000ull || pass_scratch_bytes(cn, g2, tbl->c, true) > budget;
         Plan p;
-        auto_plan(cn, g2, tn.glv_mode, tn.window_override, p);
+        auto_plan(cn, g2, tn.glv_mode, tn.window_override, p, tn.batch_affine);
         size_t ent = (p.glv ? 2 : 1) * cn;
         return ent * p.nwin >= 0xfff00000ull || cn >= (1ull << 30) || pass_scratch_bytes(cn, g2, tn.window_override) > budget;
     };
@@ -809,7 +809,7 @@ int msm_streamed(int group, DeviceCtx &cx, const Tun &tn, const void *h_bases, c
         pl.c = tbl->c;
         pl.nwin = tbl->nwin;
         pl.nbw = pl.nb = 1u << (pl.c - 1);
-    } else auto_plan(n, g2, tn.glv_mode, tn.window_override, pl);
+    } else auto_plan(n, g2, tn.glv_mode, tn.window_override, pl, tn.batch_affine);
     if (h_bases)
         if (int rc = cx.bases.reserve(n * AB)) return rc;
     if (cx.busy_valid) CUDA_TRY(cudaStreamWaitEvent(cx.stream, cx.ev_busy, 0));
@@ -1403,7 +1403,7 @@ int b200msm_plan_query(int group, size_t n, int glv_mode, int out[4]) {
     if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "bad group");
     if (!out || n == 0 || glv_mode < -1 || glv_mode > 1) return fail(B200MSM_EINVAL, "bad argument");
     Plan pl;
-    auto_plan(n, group == B200MSM_G2, glv_mode, 0, pl);   // host arithmetic only: no device needed
+    auto_plan(n, group == B200MSM_G2, glv_mode, 0, pl, tun_snapshot().batch_affine);   // host arithmetic only: no device needed
     out[0] = pl.c;
     out[1] = pl.nwin;
     out[2] = pl.glv ? (pl.split ? 2 : 1) : 0;

@@ -36,7 +36,9 @@ BaPlan ba_plan(size_t s_out_max, int sm_count) {
     size_t NT = (s_out_max + K - 1) / K;
     NT = (NT + 127) / 128 * 128;
     if (NT == 0) NT = 128;
-    size_t K2 = (NT + 16383) / 16384;
+    // second level: short chains (the level is latency-bound: K2 dependent products per thread) but few enough
+    // totals left that their divsteps inversions (≈25 k instructions each) stay around 3 warps per scheduler
+    size_t K2 = (NT + 65535) / 65536;
     K2 = K2 < 8 ? 8 : (K2 > 64 ? 64 : K2);
     bp.NT = (uint32_t)NT;
     bp.K = (uint32_t)K;

@@ -162,6 +162,14 @@ MODINV_HD void mi_inverse_u32(uint32_t out[12], const uint32_t a[12]) {
         zeta = mi_divsteps_30(zeta, (uint32_t)f.v[0], (uint32_t)g.v[0], t);
         mi_update_de(d, e, t);
         mi_update_fg(f, g, t);
+#if defined(__CUDA_ARCH__)
+        // g = 0 is a fixed point (f = ±1 and d stay as they are): stop as soon as every lane of the warp got
+        // there — typically after ≈24 of the 30 worst-case rounds
+        int32_t any = 0;
+#pragma unroll
+        for (int i = 0; i < MI_LIMBS; i++) any |= g.v[i];
+        if (__all_sync(__activemask(), any == 0)) break;
+#endif
     }
     mi_normalize(d, f.v[MI_LIMBS - 1]);
     mi_to_u32(out, d);

@@ -31,7 +31,18 @@ inline int plan_windows(bool glv, int c, bool *split) {
 // at 55 %, 3.4 µs (G1) / 11 µs (G2) per dependent doubling of the Horner chain, 23 ps per sorted
 // entry.  Without GLV this lands on the work-minimising c* of SURVEY §8(d) (13/16/18/20 at
 // 2^16/20/22/24) — the width the roofline numerator assumes.
-inline double plan_time_us(size_t n, bool g2, bool glv, int c) {
+// Batched-affine pairing rounds in front of the XYZZ accumulation (batch_affine.cuh): how many, from the mean
+// bucket occupancy (measured on B200, profiles/r02_experiments.md: three rounds pay from ≈24 entries per bucket,
+// one from ≈12; below that the padding of every bucket to 2^R entries costs more than the affine additions save),
+// and what they make of the accumulation time (measured 0.74–0.80 with three rounds, 0.93 with one).
+inline int ba_rounds_for(double avg_occupancy) { return avg_occupancy >= 24 ? 3 : (avg_occupancy >= 12 ? 1 : 0); }
+inline double ba_time_factor(double avg_occupancy, bool g2, int ba_mode) {
+    const int R = ba_mode < 0 ? ba_rounds_for(avg_occupancy) : ba_mode;
+    if (R == 0) return 1.0;
+    if (R == 1) return 0.93;
+    return g2 ? 0.75 : 0.79;
+}
+inline double plan_time_us(size_t n, bool g2, bool glv, int c, int ba_mode = -1) {
     bool split;
     const double W = plan_windows(glv, c, &split), entries = (glv ? 2.0 : 1.0) * (double)n;
     const double Wacc = split ? W - 1 : W;  // an entry lands in one of the two top windows
@@ -41,7 +52,7 @@ inline double plan_time_us(size_t n, bool g2, bool glv, int c) {
     // (GLV: the φ(P) entries read x from the β·x table and y from the base record — measured 2.5 % / 6 % slower)
     const double wps = W * std::pow(2.0, c - 1) / 32 / 592;
     const double eff = std::min(g2 ? 0.76 : 0.88, 0.35 * wps) * (glv ? (g2 ? 0.94 : 0.975) : 1.0);
-    double t = entries * Wacc * madd * 588 / (pipe * eff);
+    double t = entries * Wacc * madd * 588 / (pipe * eff) * ba_time_factor(entries / std::pow(2.0, c - 1), g2, ba_mode);
     t += W * std::pow(2.0, c - 1) * 2 * add * 588 / (pipe * 0.55);
     t += (split ? (W - 2) * c + c - 1 : (W - 1) * c) * (g2 ? 11.0 : 3.4) + 250;
     t += entries * W * 2.3e-5;
@@ -58,7 +69,7 @@ inline double plan_time_us(size_t n, bool g2, bool glv, int c) {
     }
     return t;
 }
-inline void auto_plan(size_t n, bool g2, int glv_mode, int c_override, Plan &pl) {
+inline void auto_plan(size_t n, bool g2, int glv_mode, int c_override, Plan &pl, int ba_mode = -1) {
     double best = 1e300;
     for (int glv = 0; glv <= 1; glv++) {
         if (glv_mode == 0 && glv) continue;
@@ -67,7 +78,7 @@ inline void auto_plan(size_t n, bool g2, int glv_mode, int c_override, Plan &pl)
         if (glv && 2 * n >= (1ull << 31)) continue;
         for (int c = 2; c <= 22; c++) {
             if (c_override > 0 && c != c_override) continue;
-            double t = plan_time_us(n, g2, glv, c);
+            double t = plan_time_us(n, g2, glv, c, ba_mode);
             if (t < best) { best = t; pl.c = c; pl.glv = glv; }
         }
     }

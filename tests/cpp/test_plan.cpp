@@ -35,9 +35,10 @@ int main() {
             CHECK((tc == 10 || tc == 13 || tc == 16 || tc == 20) && 255 - (tw - 1) * tc >= tc - 5);
         }
         Plan p;
-        auto_plan(1u << 16, g2, 0, 0, p); CHECK(p.c == 13 && p.nwin == 20);
-        auto_plan(1u << 20, g2, 0, 0, p); CHECK(p.c == 16 && p.nwin == 16);
-        auto_plan(1u << 24, g2, 0, 0, p); CHECK(p.c == 20 && p.nwin == 13);
+        auto_plan(1u << 16, g2, 0, 0, p, 0); CHECK(p.c == 13 && p.nwin == 20);   // (batched-affine rounds off: the plain work model)
+        auto_plan(1u << 20, g2, 0, 0, p, 0); CHECK(p.c == 16 && p.nwin == 16);
+        auto_plan(1u << 24, g2, 0, 0, p, 0); CHECK(p.c == 20 && p.nwin == 13);
+        CHECK(ba_rounds_for(64) == 3 && ba_rounds_for(16) == 1 && ba_rounds_for(4) == 0);
         auto_plan(1u << 20, g2, -1, 0, p); CHECK(p.glv && p.split && p.c == 16 && p.nwin == 9);
     }
     std::printf(failures ? "FAILED (%d)\n" : "ok\n", failures);

@@ -101,18 +101,26 @@ def _plan(eng, group, n, glv):
 
 
 def test_planner_host_logic(eng):
-    """auto_plan needs no device. Without GLV it lands on the work model's canonical c* of SURVEY
+    """auto_plan needs no device. Without GLV and without batched-affine rounds it lands on the work model's canonical c* of SURVEY
     §8(d) at 2^16 / 2^20 / 2^24 (13 / 16 / 20; 16 instead of 18 at 2^22, whose top window would be
     degenerate) with c·W ≥ 256; GLV takes c = 16 with the unsigned top digit (8 + 1 windows) where
     it was measured to pay and is never picked automatically above 2^22 points."""
     from bench import work_model
 
+    L = eng._lib.lib
     for g in (0, 1):
-        for logn, c_exp in ((16, 13), (20, 16), (22, 16), (24, 20)):
+        assert L.b200msm_set_batch_affine(0) == 0      # the canonical widths are those of the plain XYZZ accumulation
+        try:
+            for logn, c_exp in ((16, 13), (20, 16), (22, 16), (24, 20)):
+                c, W, glv, nb = _plan(eng, g, 1 << logn, 0)
+                assert (c, glv) == (c_exp, 0) and c * W >= 256 and W == -(-256 // c) and nb == W << (c - 1)
+                if logn != 22:
+                    assert c == work_model(1 << logn, g)[0]
+        finally:
+            L.b200msm_set_batch_affine(-1)
+        for logn in (16, 20, 22, 24):                   # with the batched-affine rounds the model may go one width down
             c, W, glv, nb = _plan(eng, g, 1 << logn, 0)
-            assert (c, glv) == (c_exp, 0) and c * W >= 256 and W == -(-256 // c) and nb == W << (c - 1)
-            if logn != 22:
-                assert c == work_model(1 << logn, g)[0]
+            assert glv == 0 and c * W >= 256 and W == -(-256 // c) and abs(c - work_model(1 << logn, g)[0]) <= 2
         for logn in (16, 18, 20):
             assert _plan(eng, g, 1 << logn, -1)[:3] == (16, 9, 2)
         for logn in (23, 24, 26):
