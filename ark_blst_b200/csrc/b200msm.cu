@@ -801,9 +801,40 @@ int msm_streamed(int group, DeviceCtx &cx, const Tun &tn, const void *h_bases, c
                  const uint64_t *h_scalars, size_t n, int mont) {
     const bool g2 = group == B200MSM_G2;
     const size_t AB = aff_bytes(group);
-    // ≈2^17 points per slice (measured best: 2 slices at 2^18, 4 at 2^19, 8 from 2^20 up), unless forced (stream_min < 2^17)
-    const size_t per = std::min<size_t>((size_t)1 << 17, std::max<size_t>(tn.stream_min, 1));
-    const int K = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(tn.stream_slices, 8), n / per));
+    // Slice boundaries.  From page-locked memory the copies are asynchronous and faster per point than the
+    // accumulation (128 B at ≈55 GB/s = 2.3 ns against ≈5 ns for G1, ≈19 ns for G2), so the slices GROW by that
+    // ratio: a small first slice gets the GPU going after ≈0.2 ms, each next one has landed when the previous is
+    // done, and the late, large slices hold enough entries per bucket for the batched-affine rounds (which need
+    // ≈24).  From pageable memory (a Rust Vec) the driver stages the copy at a fifth of that rate and blocks
+    // the caller — the transfer is the critical path — so the slices stay equal and small (≈2^17 points: the
+    // accumulation left after the last copy is short).  `stream_min` below 2^17 forces small equal slices (tests).
+    size_t bounds[9];
+    int K;
+    {
+        cudaPointerAttributes at;
+        const bool pinned = cudaPointerGetAttributes(&at, h_scalars) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        const size_t per = std::min<size_t>((size_t)1 << 17, std::max<size_t>(tn.stream_min, 1));
+        const int kmax = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(tn.stream_slices, 8), n / per));
+        if (!pinned || tn.stream_min < ((size_t)1 << 17) || kmax < 2) {
+            K = kmax;
+            for (int k = 0; k <= K; k++) bounds[k] = n * k / K;
+        } else {
+            const double h2d_ns = (double)(32 + (h_bases ? AB : 0)) / 55.0, acc_ns = g2 ? 19.0 : 5.0;
+            const double ratio = std::min(8.0, std::max(1.5, acc_ns / h2d_ns));
+            K = 1;
+            for (int k = 2; k <= kmax; k++) {                // as many slices as leave the first one ≥ 2^16 points
+                const double first = (double)n * (ratio - 1) / (std::pow(ratio, k) - 1);
+                if (first >= 65536.0) K = k;
+            }
+            double acc = 0, tot = (std::pow(ratio, K) - 1) / (ratio - 1);
+            bounds[0] = 0;
+            for (int k = 0; k < K; k++) {
+                acc += std::pow(ratio, k);
+                bounds[k + 1] = k == K - 1 ? n : ((size_t)((double)n * acc / tot) + 127) / 128 * 128;
+            }
+        }
+    }
     Plan pl;
     if (tbl) {  // resident fixed-base table: the table fixes the width, one bucket set
         pl.c = tbl->c;
@@ -821,7 +852,7 @@ int msm_streamed(int group, DeviceCtx &cx, const Tun &tn, const void *h_bases, c
     // stages through the driver and blocks the host, and this order keeps the GPU accumulating
     // slice k while the host is stuck copying slice k+1 (19.5 → 13.7 ms at G1 2^20 one-shot).
     for (int k = 0; k < K; k++) {
-        const size_t lo = n * k / K, hi = n * (k + 1) / K;
+        const size_t lo = bounds[k], hi = bounds[k + 1];
         CUDA_TRY(cudaMemcpyAsync((char *)cx.scalars.p + lo * 32, h_scalars + 4 * lo, (hi - lo) * 32, cudaMemcpyHostToDevice, cx.copy_stream));
         CUDA_TRY(cudaEventRecord(cx.ev_slice[2 * k], cx.copy_stream));
         if (h_bases) {

@@ -112,35 +112,9 @@ __device__ __forceinline__ void ba_load_y(const BaSrc &s, size_t pos, uint32_t v
     } else f_load(y, s.pts + pos * (2 * W) + W);
 }
 
-// pull the pair of a slot this thread visits next towards L1 while the current one is being computed
-template <class F, bool FIRST>
-__device__ __forceinline__ void ba_prefetch(const BaSrc &s, size_t slot, bool with_y) {
-    constexpr int W = field_words<F>::value;
-    if (FIRST) {
-        const uint2 v = *reinterpret_cast<const uint2 *>(s.vals + 2 * slot);
-        const uint32_t vv[2] = {v.x, v.y};
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            if (vv[k] == 0xffffffffu) continue;
-            uint32_t idx = vv[k] & 0x7fffffffu;
-            const bool endo = idx >= s.n_pts;
-            if (endo) idx -= s.n_pts;
-            const char *p = reinterpret_cast<const char *>(s.pts + (size_t)idx * (2 * W));
-            const char *px = endo ? reinterpret_cast<const char *>(s.endo_x + (size_t)idx * W) : p;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(px));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(px + 4 * W - 4));
-            if (with_y) {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 4 * W));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 8 * W - 4));
-            }
-        }
-    } else {
-        const char *p = reinterpret_cast<const char *>(s.pts + 2 * slot * (2 * W));
-#pragma unroll
-        for (int k = 0; k < 16 * W; k += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + k));
-    }
-}
-
+// (A software prefetch of the next slot's pair — vals, then prefetch.global.L1 of both points — was measured on
+// B200 and is SLOWER: G1 2^20 accumulate 5.02 → 5.10 ms, 2^24 61.3 → 78.0 ms; at 2^24 the prefetched lines are
+// evicted before their use and the gather's DRAM traffic doubles.  profiles/r02_experiments.md)
 enum { BA_NONE = 0, BA_FIRST = 1, BA_SECOND = 2, BA_ADD = 3, BA_DBL = 4, BA_CANCEL = 5 };
 
 // slots of a thread: t, t + NT, t + 2·NT, …  A warp stops at the first j whose 32 slots all lie past the end.
@@ -166,7 +140,6 @@ k_ba_fwd(BaSrc s, const uint32_t *__restrict__ total_ptr, int shift, uint32_t NT
         const uint32_t slot = j * NT + t;
         F d;
         f_set_one(d);
-        if (j + 1 < trips && slot + NT < S_out) ba_prefetch<F, FIRST>(s, (size_t)slot + NT, false);
         if (slot < S_out) {
             F x1, x2;
             uint32_t v1 = 0, v2 = 0;
@@ -205,7 +178,6 @@ k_ba_bwd(BaSrc s, const uint32_t *__restrict__ total_ptr, int shift, uint32_t NT
         F x1, y1, x2, y2, d, num;
         int kind = BA_NONE;
         f_set_one(d);
-        if (j > 0 && slot - NT < S_out) ba_prefetch<F, FIRST>(s, (size_t)slot - NT, true);
         if (slot < S_out) {
             uint32_t v1 = 0, v2 = 0;
             const bool h1 = ba_load_x<F, FIRST>(s, 2 * (size_t)slot, x1, v1);
