@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -194,6 +195,20 @@ struct Engine {
     std::mutex multi_mu;              // one sharded (multi-device) call at a time: they share the gather slots
     std::mutex tun_mu;
     Tun tun;
+    // A process that bound several devices and exits without b200msm_shutdown must not die in ~std::thread of a
+    // worker that is still waiting for work: stop and join them (they touch no CUDA state on the way out).
+    ~Engine() { stop_workers(); }
+    void stop_workers() {
+        for (auto &w : workers) {
+            {
+                std::lock_guard<std::mutex> wl(w->mu);
+                w->quit = true;
+                w->cv.notify_all();
+            }
+            if (w->th.joinable()) w->th.join();
+        }
+        workers.clear();
+    }
 };
 Engine g_eng;
 Tun tun_snapshot() {
@@ -946,6 +961,12 @@ int device_share(DeviceCtx &cx, const Share &sh) {
 // parallel (a streamed share is ≈ 300 launches and, from pageable memory, blocking staged
 // copies — issued device after device from one thread they would serialise), each sends its
 // partial to device 0 over NVLink, and the caller adds the partials there.
+static const bool g_trace = getenv("B200MSM_TRACE") != nullptr;   // host-side timeline of a sharded call on stderr (development aid)
+static double now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 void DeviceWorker::loop() {
         cudaSetDevice(cx->dev);
         for (;;) {
@@ -955,6 +976,7 @@ void DeviceWorker::loop() {
             const Share *sh = job;
             lk.unlock();
             int r;
+            const double tw0 = now_ms();
             {
                 std::lock_guard<std::mutex> cl(cx->mu);
                 r = device_share(*cx, *sh);
@@ -968,6 +990,11 @@ void DeviceWorker::loop() {
                     if (e != cudaSuccess) r = fail(B200MSM_ECUDA, std::string("cudaEventRecord: ") + cudaGetErrorString(e));
                 }
                 if (r) drain(*cx);
+            }
+            if (g_trace) {
+                const double tw1 = now_ms();
+                cudaStreamSynchronize(cx->stream);
+                fprintf(stderr, "[b200msm trace] dev %d: issue %.3f ms (from %.3f), device done +%.3f ms\n", cx->dev, tw1 - tw0, tw0, now_ms() - tw1);
             }
             lk.lock();
             rc = r;
@@ -1033,6 +1060,7 @@ int msm_host(int group, const uint64_t *bases, const uint64_t *scalars, size_t n
             cudaSetDevice(cx.dev);
             rc = cx.out.reserve(JB * (size_t)(ndev + 1));
         }
+        const double tm0 = now_ms();
         if (!rc) {
             for (int d = 0; d < ndev; d++) {
                 DeviceWorker &w = *g_eng.workers[d];
@@ -1049,8 +1077,10 @@ int msm_host(int group, const uint64_t *bases, const uint64_t *scalars, size_t n
                 w.cv.wait(lk, [&] { return w.done; });
                 if (w.rc && !rc) rc = fail(w.rc, w.err);
             }
+            const double tm1 = now_ms();
             std::lock_guard<std::mutex> lk(c0.mu);
             cudaSetDevice(c0.dev);
+            if (g_trace) fprintf(stderr, "[b200msm trace] posted at %.3f, all shares issued +%.3f ms\n", tm0, tm1 - tm0);
             if (!rc) {
                 // device 0 waits for every share (its own included), adds the partials, downloads
                 cudaError_t e = cudaSuccess;
@@ -1061,6 +1091,7 @@ int msm_host(int group, const uint64_t *bases, const uint64_t *scalars, size_t n
                     e = cudaMemcpyAsync(out, sum, JB, cudaMemcpyDeviceToHost, c0.stream);
                 }
                 if (e == cudaSuccess) e = cudaStreamSynchronize(c0.stream);
+                if (g_trace) fprintf(stderr, "[b200msm trace] combined on device 0 +%.3f ms after issue\n", now_ms() - tm1);
                 if (e != cudaSuccess) rc = fail(B200MSM_ECUDA, std::string("msm combine: ") + cudaGetErrorString(e));
                 // the other devices are idle now (device 0 waited for them), but say so to their contexts:
                 // the caller's buffers must not be in use once we return
@@ -1093,15 +1124,7 @@ void b200msm_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_eng.mu);
     int prev = 0;
     cudaGetDevice(&prev);
-    for (auto &w : g_eng.workers) {
-        {
-            std::lock_guard<std::mutex> wl(w->mu);
-            w->quit = true;
-            w->cv.notify_all();
-        }
-        w->th.join();
-    }
-    g_eng.workers.clear();
+    g_eng.stop_workers();
     for (auto &c : g_eng.ctx) destroy_ctx(*c);
     for (auto &c : g_eng.lane_ctx) destroy_ctx(*c);
     g_eng.lane_ctx.clear();

@@ -266,6 +266,9 @@ class Ctx:
 
             dist.init_process_group("nccl", device_id=self.dev)
             self.dist = dist
+            # a CPU-side group for waits that must leave the GPUs idle (an NCCL barrier parks a spinning kernel on every
+            # waiting rank's GPU, and kernels of another process then time-slice against it)
+            self.cpu_group = dist.new_group(backend="gloo")
         self.L = eng._lib.lib
         eng._lib.check(self.L.b200msm_init(self.local, 1), "init")
         self.stream = torch.cuda.current_stream().cuda_stream
@@ -276,6 +279,11 @@ class Ctx:
         if self.dist:
             self.dist.barrier()
         self.torch.cuda.synchronize()
+
+    def cpu_barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist:
+            self.dist.barrier(group=self.cpu_group)
 
     def allmax(self, x):
         t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
@@ -794,9 +802,11 @@ def run_ours(args):
         extra_blocks["groth16_2p22"] = {"uniform": block_groth16(cx, args, 22, "uniform"),
                                         "witness_like": block_groth16(cx, args, 22, "witness")}
     if "single_process" in blocks and world > 1:
+        # the other ranks wait on the CPU (gloo), GPUs idle: the child process drives all N GPUs itself
         cx.barrier()
+        cx.cpu_barrier()
         sp = block_single_process(args, world) if rank == 0 else None
-        cx.barrier()
+        cx.cpu_barrier()
         if rank == 0:
             extra_blocks["single_process"] = sp
 
