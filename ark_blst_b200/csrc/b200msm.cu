@@ -719,11 +719,12 @@ int run_group(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases, cons
     size_t chunks = 1;
     auto too_big = [&](size_t cn) {
         if (tn.max_chunk_override) return cn > tn.max_chunk_override;
-        if (tbl) return cn * tbl->nwin >= 0xfff00000ull || pass_scratch_bytes(cn, g2, tbl->c, true) > budget;
+        // (positions in the sorted entry array are 32-bit; the batched-affine padding adds up to 7 slots per bucket)
+        if (tbl) return cn * tbl->nwin + ((size_t)7 << (tbl->c - 1)) >= 0xfff00000ull || pass_scratch_bytes(cn, g2, tbl->c, true) > budget;
         Plan p;
         auto_plan(cn, g2, tn.glv_mode, tn.window_override, p, tn.batch_affine);
         size_t ent = (p.glv ? 2 : 1) * cn;
-        return ent * p.nwin >= 0xfff00000ull || cn >= (1ull << 30) || pass_scratch_bytes(cn, g2, tn.window_override) > budget;
+        return ent * p.nwin + (size_t)p.nb * 7 >= 0xfff00000ull || cn >= (1ull << 30) || pass_scratch_bytes(cn, g2, tn.window_override) > budget;
     };
     while (too_big((n + chunks - 1) / chunks)) {
         chunks *= 2;
@@ -836,9 +837,11 @@ int msm_streamed(int group, DeviceCtx &cx, const Tun &tn, const void *h_bases, c
             for (int k = 0; k <= K; k++) bounds[k] = n * k / K;
         } else {
             const double h2d_ns = (double)(32 + (h_bases ? AB : 0)) / 55.0, acc_ns = g2 ? 19.0 : 5.0;
-            const double ratio = std::min(8.0, std::max(1.5, acc_ns / h2d_ns));
+            static const double env_ratio = getenv("B200MSM_SLICE_RATIO") ? atof(getenv("B200MSM_SLICE_RATIO")) : 0;   // (sweeps)
+            static const int env_k = getenv("B200MSM_SLICE_K") ? atoi(getenv("B200MSM_SLICE_K")) : 0;
+            const double ratio = env_ratio > 1 ? env_ratio : std::min(8.0, std::max(1.5, acc_ns / h2d_ns));
             K = 1;
-            for (int k = 2; k <= kmax; k++) {                // as many slices as leave the first one ≥ 2^16 points
+            for (int k = 2; k <= (env_k ? std::min(env_k, kmax) : kmax); k++) {   // as many slices as leave the first one ≥ 2^16 points
                 const double first = (double)n * (ratio - 1) / (std::pow(ratio, k) - 1);
                 if (first >= 65536.0) K = k;
             }

@@ -7,7 +7,10 @@ void launch_wsum_level_g1(const uint32_t *X, const uint32_t *Cin, uint32_t len, 
                           uint32_t *Rout, uint32_t *Cout, cudaStream_t st) {
     count_launch();
     uint32_t nseg = len / m;
-    k_wsum_level<fp><<<blocks_for((size_t)nseg * nwin * 4, 128), 128, 0, st>>>(X, Cin, len, m, log2M, nwin, Rout, Cout);
+    if ((size_t)nseg * nwin >= WSUM_THREAD_FORM_MIN)   // enough chains to fill the GPU with one thread each (reduce.cuh)
+        k_wsum_level_thread<fp><<<blocks_for((size_t)nseg * nwin, 128), 128, 0, st>>>(X, Cin, len, m, log2M, nwin, Rout, Cout);
+    else
+        k_wsum_level<fp><<<blocks_for((size_t)nseg * nwin * 4, 128), 128, 0, st>>>(X, Cin, len, m, log2M, nwin, Rout, Cout);
 }
 void launch_tree_level_g1(const uint32_t *Sin, size_t sin_stride, const uint32_t *Vin, const uint32_t *Cin, size_t cin_stride,
                           uint32_t *Sout, uint32_t *Vout, uint32_t *Cout, size_t out_stride, uint32_t S, int j, uint32_t nwin,

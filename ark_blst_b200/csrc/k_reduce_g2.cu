@@ -7,6 +7,7 @@ void launch_wsum_level_g2(const uint32_t *X, const uint32_t *Cin, uint32_t len, 
                           uint32_t *Rout, uint32_t *Cout, cudaStream_t st) {
     count_launch();
     uint32_t nseg = len / m;
+    // (G2 stays in quad form at every size: three XYZZ values over Fp2 are 288 registers — the thread form spills 1.5 KB)
     k_wsum_level<fp2><<<blocks_for((size_t)nseg * nwin * 4, 128), 128, 0, st>>>(X, Cin, len, m, log2M, nwin, Rout, Cout);
 }
 void launch_tree_level_g2(const uint32_t *Sin, size_t sin_stride, const uint32_t *Vin, const uint32_t *Cin, size_t cin_stride,

@@ -67,6 +67,7 @@ void launch_table_shift_g1(const uint32_t *prev, size_t n, int c, uint32_t *jac_
 void launch_table_shift_g2(const uint32_t *prev, size_t n, int c, uint32_t *jac_out, cudaStream_t st);
 
 // k_reduce_g{1,2}.cu
+constexpr size_t WSUM_THREAD_FORM_MIN = 131072;   // chains from which a running-sum level runs one thread per chain instead of a quad
 void launch_wsum_level_g1(const uint32_t *X, const uint32_t *Cin, uint32_t len, uint32_t m, int log2M, uint32_t nwin,
                           uint32_t *Rout, uint32_t *Cout, cudaStream_t st);
 void launch_wsum_level_g2(const uint32_t *X, const uint32_t *Cin, uint32_t len, uint32_t m, int log2M, uint32_t nwin,

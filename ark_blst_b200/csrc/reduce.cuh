@@ -48,6 +48,40 @@ k_wsum_level(const uint32_t *__restrict__ X, const uint32_t *__restrict__ Cin, u
     if (live) q_store(Cout + ((size_t)w * nseg + s) * PW, acc);
 }
 
+// The same level with ONE THREAD per (window, segment) instead of a quad: with ≥ 10^5 chains in flight the level is
+// throughput-bound, and the thread form (inlined XYZZ additions, the accumulation kernel's shape) runs closer to
+// the pipe than the quad form, whose 14 products per addition occupy 16 lane-slots and pay 6 shuffles of 12 words.
+// Used by run_pass from 131 072 chains up (G1 2^24: 213 k chains, 9.8 → see profiles/r02_experiments.md).
+template <class F>
+__global__ void __launch_bounds__(128, 2)
+k_wsum_level_thread(const uint32_t *__restrict__ X, const uint32_t *__restrict__ Cin, uint32_t len, uint32_t m,
+                    int log2M, uint32_t nwin, uint32_t *__restrict__ Rout, uint32_t *__restrict__ Cout) {
+    constexpr int PW = 4 * field_words<F>::value;
+    const uint32_t nseg = len / m;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nseg * nwin) return;
+    const uint32_t w = t / nseg, s = t % nseg;
+    const uint32_t *x = X + ((size_t)w * len + (size_t)s * m) * PW;
+    xyzz<F> run, acc, tmp;
+    xyzz_set_inf(run);
+    xyzz_set_inf(acc);
+    for (uint32_t j = m; j-- > 0;) {
+        xyzz_load(tmp, x + (size_t)j * PW);
+        xyzz_add(run, tmp);                        // inlined: the operands stay in registers
+        if (j) xyzz_add(acc, run);                 // element 0 has weight 0
+    }
+    xyzz_store(Rout + ((size_t)w * nseg + s) * PW, run);
+    for (int k = 0; k < log2M; k++) xyzz_dbl_ni(acc);
+    if (Cin) {
+        const uint32_t *ci = Cin + ((size_t)w * len + (size_t)s * m) * PW;
+        for (uint32_t j = 0; j < m; j++) {
+            xyzz_load(tmp, ci + (size_t)j * PW);
+            xyzz_add_ni(acc, tmp);
+        }
+    }
+    xyzz_store(Cout + ((size_t)w * nseg + s) * PW, acc);
+}
+
 // ---- upper part of the reduction: a log-depth tree instead of more running-sum levels --------
 // For X[0..S) per window, Wsum0(X) = Σ_k 2^k·V_k with V_k = Σ_{i: bit k of i set} X_i.  A node
 // covering 2^j consecutive elements keeps its sum and its j partial V's; merging two siblings is

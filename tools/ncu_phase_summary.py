@@ -9,8 +9,10 @@ import subprocess
 import sys
 
 tag, rep, tkey = sys.argv[1], sys.argv[2], sys.argv[3]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
+# `rep` is either a .ncu-rep or the CSV of `ncu -i <rep> --page raw --csv` (the reports of 20 kernels exceed what
+# gpurun copies back, so the CSV is made on the GPU box)
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(l for l in raw.splitlines() if l.startswith('"')))
 hdr, units = rows[0], rows[1]
 ui = dict(zip(hdr, units))
 keep = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__occupancy_limit_registers",
