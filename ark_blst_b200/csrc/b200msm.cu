@@ -433,11 +433,15 @@ int pass_prepare(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v,
         if (int rc = cx.endo.reserve(n * (size_t)W * 4)) return rc;
     if (R > 0) {
         const size_t FB = (size_t)W * 4, s1 = (slots_max + 1) / 2;
-        const BaPlan bp = ba_plan(s1, cx.sm_count);
-        if (int rc = cx.ba_prefix.reserve(((size_t)bp.NT * bp.K + 4096) * FB)) return rc;
-        if (int rc = cx.ba_T.reserve(((size_t)bp.NT + 256) * FB)) return rc;
-        if (int rc = cx.ba_prefix2.reserve(((size_t)bp.NT + 256) * FB)) return rc;
-        if (int rc = cx.ba_U.reserve(((size_t)bp.NU + 64) * FB)) return rc;
+        // round 1 is the largest; it may run unsplit or as two half-range pipelines (pass_issue_main), whose plans
+        // round up separately and may use a smaller K (more threads): reserve for whichever is larger
+        const BaPlan bp = ba_plan(s1, cx.sm_count), bh = ba_plan(s1 / 2 + ((size_t)1 << (5 + R)) + 1, cx.sm_count);
+        const size_t pre_el = std::max((size_t)bp.NT * bp.K, 2 * (size_t)bh.NT * bh.K) + 65536;
+        const size_t t_el = std::max<size_t>(bp.NT, 2 * (size_t)bh.NT) + 4096, u_el = std::max<size_t>(bp.NU, 2 * (size_t)bh.NU) + 1024;
+        if (int rc = cx.ba_prefix.reserve(pre_el * FB)) return rc;
+        if (int rc = cx.ba_T.reserve(t_el * FB)) return rc;
+        if (int rc = cx.ba_prefix2.reserve(t_el * FB)) return rc;
+        if (int rc = cx.ba_U.reserve(u_el * FB)) return rc;
         if (int rc = cx.ba_pts[0].reserve(s1 * 2 * FB)) return rc;
         if (R > 1)
             if (int rc = cx.ba_pts[1].reserve((s1 + 1) / 2 * 2 * FB)) return rc;
@@ -497,13 +501,34 @@ int pass_issue_main(DeviceCtx &cx, const PassArgs &pa, cudaStream_t st, bool pro
         const size_t entries = pa.glv ? 2 * pa.n : pa.n, m = entries * (size_t)pa.nwin;
         size_t s_out = (m + (size_t)pa.nb * ((1u << pa.R) - 1) + 1) / 2;
         const uint32_t *src = pa.d_bases;
+        // Large rounds run as TWO interleaved pipelines over the two halves of the slot range, on two streams: the
+        // second level + inversion of a round are three small latency-bound launches (≈0.1–0.2 ms in all) during
+        // which a single pipeline leaves the GPU almost idle; with two, the other half's large kernels fill it.
+        static const bool split_ok = !(getenv("B200MSM_BA_SPLIT") && atoi(getenv("B200MSM_BA_SPLIT")) == 0);
+        const bool split = split_ok && s_out >= ((size_t)1 << 20);
+        const int align_log = split ? 6 + pa.R : 0;
+        const size_t FW = (size_t)W;   // u32 words per field element
+        if (split) {
+            CUDA_TRY(cudaEventRecord(cx.ev_fork, st));
+            CUDA_TRY(cudaStreamWaitEvent(cx.aux_stream, cx.ev_fork, 0));
+        }
         for (int r = 0; r < pa.R; r++) {
-            const BaPlan bp = ba_plan(s_out, cx.sm_count);
             uint32_t *out = cx.ba_pts[r & 1].as<uint32_t>();
-            (g2 ? launch_ba_round_g2 : launch_ba_round_g1)(r == 0, src, vals, endo_x, n_pts, start + pa.nb, r, bp, cx.ba_prefix.as<uint32_t>(),
-                                                           cx.ba_T.as<uint32_t>(), cx.ba_prefix2.as<uint32_t>(), cx.ba_U.as<uint32_t>(), out, st);
+            const size_t s_part = split ? s_out / 2 + ((size_t)1 << (5 + pa.R)) + 1 : s_out;
+            const BaPlan bp = ba_plan(s_part, cx.sm_count);
+            for (int part = 0; part < (split ? 2 : 1); part++) {
+                const size_t o1 = part ? (size_t)bp.NT * bp.K : 0, o2 = part ? bp.NT : 0, o3 = part ? bp.NU : 0;
+                (g2 ? launch_ba_round_g2 : launch_ba_round_g1)(r == 0, src, vals, endo_x, n_pts, start + pa.nb, r, bp,
+                                                               cx.ba_prefix.as<uint32_t>() + o1 * FW, cx.ba_T.as<uint32_t>() + o2 * FW,
+                                                               cx.ba_prefix2.as<uint32_t>() + o2 * FW, cx.ba_U.as<uint32_t>() + o3 * FW, out,
+                                                               part ? cx.aux_stream : st, part, align_log);
+            }
             src = out;
             s_out = (s_out + 1) / 2;
+        }
+        if (split) {
+            CUDA_TRY(cudaEventRecord(cx.ev_join, cx.aux_stream));
+            CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_join, 0));
         }
         acc_pts = src;
         acc_vals = nullptr;
@@ -818,7 +843,7 @@ int msm_streamed(int group, DeviceCtx &cx, const Tun &tn, const void *h_bases, c
     const bool g2 = group == B200MSM_G2;
     const size_t AB = aff_bytes(group);
     // Slice boundaries.  From page-locked memory the copies are asynchronous and faster per point than the
-    // accumulation (128 B at ≈55 GB/s = 2.3 ns against ≈5 ns for G1, ≈19 ns for G2), so the slices GROW by that
+    // accumulation (128 B at ≈55 GB/s = 2.3 ns against ≈7 ns for G1, ≈26 ns for G2 when sliced), so the slices GROW by that
     // ratio: a small first slice gets the GPU going after ≈0.2 ms, each next one has landed when the previous is
     // done, and the late, large slices hold enough entries per bucket for the batched-affine rounds (which need
     // ≈24).  From pageable memory (a Rust Vec) the driver stages the copy at a fifth of that rate and blocks
@@ -836,7 +861,7 @@ int msm_streamed(int group, DeviceCtx &cx, const Tun &tn, const void *h_bases, c
             K = kmax;
             for (int k = 0; k <= K; k++) bounds[k] = n * k / K;
         } else {
-            const double h2d_ns = (double)(32 + (h_bases ? AB : 0)) / 55.0, acc_ns = g2 ? 19.0 : 5.0;
+            const double h2d_ns = (double)(32 + (h_bases ? AB : 0)) / 55.0, acc_ns = g2 ? 26.0 : 7.0;   // (sliced accumulation: ≈7 ns per G1 point; measured best ratio 3 one-shot, 7–8 with resident bases)
             static const double env_ratio = getenv("B200MSM_SLICE_RATIO") ? atof(getenv("B200MSM_SLICE_RATIO")) : 0;   // (sweeps)
             static const int env_k = getenv("B200MSM_SLICE_K") ? atoi(getenv("B200MSM_SLICE_K")) : 0;
             const double ratio = env_ratio > 1 ? env_ratio : std::min(8.0, std::max(1.5, acc_ns / h2d_ns));

@@ -125,14 +125,29 @@ __device__ __forceinline__ uint32_t ba_trip_count(uint32_t t, uint32_t NT, uint3
     return j < K ? j : K;
 }
 
+// Slot range of one launch.  Unsplit (split_align_log = 0): all S = total ≫ shift output slots of the round.  Split in
+// two parts (run_pass runs them as two interleaved pipelines on two streams, so that the latency-bound second
+// level + inversion of one part hides under the other part's large kernels): the boundary is half the entry count
+// rounded down to a multiple of 2^split_align_log entries — a multiple of 64·2^R, so it falls on a bucket-aligned,
+// warp-aligned slot in every round, and part p of round r+1 reads exactly what part p of round r wrote.
+__device__ __forceinline__ void ba_range(const uint32_t *total_ptr, int shift, int part, int split_align_log, uint32_t &lo,
+                                         uint32_t &S_out) {
+    const uint32_t total = *total_ptr, S_all = total >> shift;
+    if (split_align_log == 0) { lo = 0; S_out = S_all; return; }
+    const uint32_t b = ((total >> 1) & ~((1u << split_align_log) - 1)) >> shift;
+    lo = part ? b : 0;
+    S_out = (part ? S_all : b) - lo;
+}
+
 template <class F, bool FIRST>
 __global__ void __launch_bounds__(128)
-k_ba_fwd(BaSrc s, const uint32_t *__restrict__ total_ptr, int shift, uint32_t NT, uint32_t K,
+k_ba_fwd(BaSrc s, const uint32_t *__restrict__ total_ptr, int shift, int part, int split_align_log, uint32_t NT, uint32_t K,
          uint32_t *__restrict__ prefix, uint32_t *__restrict__ T) {
     constexpr int W = field_words<F>::value;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= NT) return;
-    const uint32_t S_out = *total_ptr >> shift;
+    uint32_t lo, S_out;
+    ba_range(total_ptr, shift, part, split_align_log, lo, S_out);
     const uint32_t trips = ba_trip_count(t, NT, K, S_out);
     F acc;
     f_set_one(acc);
@@ -143,14 +158,15 @@ k_ba_fwd(BaSrc s, const uint32_t *__restrict__ total_ptr, int shift, uint32_t NT
         if (slot < S_out) {
             F x1, x2;
             uint32_t v1 = 0, v2 = 0;
-            const bool h1 = ba_load_x<F, FIRST>(s, 2 * (size_t)slot, x1, v1);
-            const bool h2 = ba_load_x<F, FIRST>(s, 2 * (size_t)slot + 1, x2, v2);
+            const size_t g = (size_t)lo + slot;   // slot of the whole round: positions 2g, 2g + 1 of the round's input
+            const bool h1 = ba_load_x<F, FIRST>(s, 2 * g, x1, v1);
+            const bool h2 = ba_load_x<F, FIRST>(s, 2 * g + 1, x2, v2);
             if (h1 && h2) {
                 f_sub(d, x2, x1);
                 if (f_is_zero(d)) {               // same x: doubling (d = 2y) or cancellation (d = 1); rare
                     F y1, y2;
-                    ba_load_y<F, FIRST>(s, 2 * (size_t)slot, v1, y1);
-                    ba_load_y<F, FIRST>(s, 2 * (size_t)slot + 1, v2, y2);
+                    ba_load_y<F, FIRST>(s, 2 * g, v1, y1);
+                    ba_load_y<F, FIRST>(s, 2 * g + 1, v2, y2);
                     if (f_eq(y1, y2) && !f_is_zero(y1)) f_dbl(d, y1);
                     else f_set_one(d);
                 }
@@ -164,12 +180,13 @@ k_ba_fwd(BaSrc s, const uint32_t *__restrict__ total_ptr, int shift, uint32_t NT
 
 template <class F, bool FIRST>
 __global__ void __launch_bounds__(128)
-k_ba_bwd(BaSrc s, const uint32_t *__restrict__ total_ptr, int shift, uint32_t NT, uint32_t K,
+k_ba_bwd(BaSrc s, const uint32_t *__restrict__ total_ptr, int shift, int part, int split_align_log, uint32_t NT, uint32_t K,
          const uint32_t *__restrict__ prefix, const uint32_t *__restrict__ Tinv, uint32_t *__restrict__ out) {
     constexpr int W = field_words<F>::value;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= NT) return;
-    const uint32_t S_out = *total_ptr >> shift;
+    uint32_t lo, S_out;
+    ba_range(total_ptr, shift, part, split_align_log, lo, S_out);
     const uint32_t trips = ba_trip_count(t, NT, K, S_out);
     F inv;
     f_load(inv, Tinv + (size_t)t * W);
@@ -180,10 +197,11 @@ k_ba_bwd(BaSrc s, const uint32_t *__restrict__ total_ptr, int shift, uint32_t NT
         f_set_one(d);
         if (slot < S_out) {
             uint32_t v1 = 0, v2 = 0;
-            const bool h1 = ba_load_x<F, FIRST>(s, 2 * (size_t)slot, x1, v1);
-            const bool h2 = ba_load_x<F, FIRST>(s, 2 * (size_t)slot + 1, x2, v2);
-            if (h1) ba_load_y<F, FIRST>(s, 2 * (size_t)slot, v1, y1);
-            if (h2) ba_load_y<F, FIRST>(s, 2 * (size_t)slot + 1, v2, y2);
+            const size_t g = (size_t)lo + slot;
+            const bool h1 = ba_load_x<F, FIRST>(s, 2 * g, x1, v1);
+            const bool h2 = ba_load_x<F, FIRST>(s, 2 * g + 1, x2, v2);
+            if (h1) ba_load_y<F, FIRST>(s, 2 * g, v1, y1);
+            if (h2) ba_load_y<F, FIRST>(s, 2 * g + 1, v2, y2);
             kind = h1 ? (h2 ? BA_ADD : BA_FIRST) : (h2 ? BA_SECOND : BA_NONE);
             if (kind == BA_ADD) {
                 f_sub(d, x2, x1);
@@ -208,7 +226,7 @@ k_ba_bwd(BaSrc s, const uint32_t *__restrict__ total_ptr, int shift, uint32_t NT
         f_mul(dinv, inv, pre);                    // 1/d of this slot
         f_mul(inv, inv, d);                       // inverse of the product of the slots before it
         if (slot >= S_out) continue;
-        uint32_t *o = out + (size_t)slot * (2 * W);
+        uint32_t *o = out + ((size_t)lo + slot) * (2 * W);
         if (kind == BA_ADD || kind == BA_DBL) {
             F lam, x3;
             f_mul(lam, num, dinv);

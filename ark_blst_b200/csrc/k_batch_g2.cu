@@ -5,18 +5,18 @@
 namespace b200msm {
 void launch_ba_round_g2(int first, const uint32_t *src, const uint32_t *vals, const uint32_t *endo_x, uint32_t n_pts,
                         const uint32_t *total_ptr, int round, const BaPlan &bp, uint32_t *prefix, uint32_t *T, uint32_t *prefix2,
-                        uint32_t *U, uint32_t *out, cudaStream_t st) {
+                        uint32_t *U, uint32_t *out, cudaStream_t st, int part, int split_align_log) {
     for (int k = 0; k < 5; k++) count_launch();
     BaSrc s{src, vals, endo_x, n_pts};
     const int shift = round + 1;
     const unsigned blocks = blocks_for(bp.NT, 128);
-    if (first) k_ba_fwd<fp2, true><<<blocks, 128, 0, st>>>(s, total_ptr, shift, bp.NT, bp.K, prefix, T);
-    else k_ba_fwd<fp2, false><<<blocks, 128, 0, st>>>(s, total_ptr, shift, bp.NT, bp.K, prefix, T);
+    if (first) k_ba_fwd<fp2, true><<<blocks, 128, 0, st>>>(s, total_ptr, shift, part, split_align_log, bp.NT, bp.K, prefix, T);
+    else k_ba_fwd<fp2, false><<<blocks, 128, 0, st>>>(s, total_ptr, shift, part, split_align_log, bp.NT, bp.K, prefix, T);
     k_ba_prod_fwd<fp2><<<blocks_for(bp.NU, 128), 128, 0, st>>>(T, bp.NT, bp.NU, bp.K2, prefix2, U);
     k_ba_invert<fp2><<<blocks_for(bp.NU, 64), 64, 0, st>>>(U, bp.NU);
     k_ba_prod_bwd<fp2><<<blocks_for(bp.NU, 128), 128, 0, st>>>(T, bp.NT, bp.NU, bp.K2, prefix2, U);
-    if (first) k_ba_bwd<fp2, true><<<blocks, 128, 0, st>>>(s, total_ptr, shift, bp.NT, bp.K, prefix, T, out);
-    else k_ba_bwd<fp2, false><<<blocks, 128, 0, st>>>(s, total_ptr, shift, bp.NT, bp.K, prefix, T, out);
+    if (first) k_ba_bwd<fp2, true><<<blocks, 128, 0, st>>>(s, total_ptr, shift, part, split_align_log, bp.NT, bp.K, prefix, T, out);
+    else k_ba_bwd<fp2, false><<<blocks, 128, 0, st>>>(s, total_ptr, shift, part, split_align_log, bp.NT, bp.K, prefix, T, out);
 }
 void launch_accumulate_direct_g2(const uint32_t *pts, const uint32_t *start, const uint32_t *order, uint32_t nb, uint32_t heavy_thr,
                                  int shift, int into, uint32_t *buckets, cudaStream_t st) {
