@@ -455,7 +455,7 @@ int pass_prepare(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v,
             if (int rc = cx.treeV[i].reserve((size_t)rwin * tstride * PB)) return rc;
             if (int rc = cx.treeC[i].reserve((size_t)rwin * tstride * PB)) return rc;
         }
-        if (int rc = cx.wsum.reserve((size_t)rwin * PB)) return rc;
+        if (int rc = cx.wsum.reserve(((size_t)rwin + 1) * PB)) return rc;   // (+1: k_combine parks the split top digit's term there)
     }
     pa.arena = cx.arena_epoch();
     return 0;

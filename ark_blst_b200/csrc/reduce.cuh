@@ -142,6 +142,16 @@ k_combine(const uint32_t *__restrict__ Sroot, const uint32_t *__restrict__ V, co
     constexpr int PW = 4 * W;
     const int qd = threadIdx.x >> 2;
     F acc, a;
+    // split_top: the upper half of the unsigned top digit adds 2^(c−1)·Σ buckets of the last window.  Its c − 1 dependent
+    // doublings run on WARP 3 (idle whenever nwin ≤ 24 — and split_top means c | 128, c ≥ 8, nwin ≤ 17) next to the
+    // window values instead of after them on everybody's critical path (−50 µs at c = 16); the result goes to
+    // wsum[nwin] and is added when the Horner chain starts.
+    const bool top_aside = split_top && nwin <= 24;
+    if (top_aside && threadIdx.x >= 96) {          // warp-uniform: the whole warp runs the chain, quad 24 stores
+        q_load(a, Sroot + (size_t)(nwin - 1) * stride * PW);
+        for (int k = 0; k < c - 1; k++) q_dbl(a);
+        if (qd == 24) q_store(wsum + (size_t)nwin * PW, a);
+    } else
     for (int base = 0; base < nwin; base += 32) {  // block-uniform trip count
         const int w = base + qd < nwin ? base + qd : 0;  // surplus quads recompute window 0
         q_set_inf(acc);
@@ -158,7 +168,7 @@ k_combine(const uint32_t *__restrict__ Sroot, const uint32_t *__restrict__ V, co
         }
         q_load(a, Sroot + (size_t)w * stride * PW);
         q_add(acc, a);
-        if (split_top) {                           // upper half of the unsigned top digit: + 2^(c−1)·Σ buckets
+        if (split_top && !top_aside) {             // upper half of the unsigned top digit: + 2^(c−1)·Σ buckets
             const bool extra = w == nwin - 1;      // (every quad runs the chain: q_dbl needs whole warps)
             for (int k = 0; k < c - 1; k++) q_dbl(a);
             F zero;
@@ -174,6 +184,10 @@ k_combine(const uint32_t *__restrict__ Sroot, const uint32_t *__restrict__ V, co
     int top = nwin - 1;
     if (split_top) {                               // the two halves of the top digit share one weight
         q_load(acc, wsum + (size_t)top * PW);
+        if (top_aside) {
+            q_load(a, wsum + (size_t)nwin * PW);
+            q_add(acc, a);
+        }
         top--;
     }
     for (int ww = top; ww >= 0; ww--) {
