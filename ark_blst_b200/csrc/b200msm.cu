@@ -121,7 +121,7 @@ struct DeviceCtx {
     int fits_tbl_c[2] = {0, 0};
     DevBuf bases, scalars, digits, vals, start, cnt, ord, buckets, lvlR[2], lvlC[2], out;
     DevBuf hvy_hdr, hvy_buckets, hvy_tasks, hvy_partials, treeS[2], treeV[2], treeC[2], wsum, chunk_partials, norm_in, norm_out, tile_sums, size_hist, endo, tbl_tmp;
-    DevBuf ba_prefix, ba_T, ba_prefix2, ba_U, ba_pts[2];   // batched-affine rounds (batch_affine.cuh)
+    DevBuf ba_prefix, ba_T, ba_prefix2, ba_U, ba_pts[3];   // (one output array per round: the two half-range pipelines may be a round apart)   // batched-affine rounds (batch_affine.cuh)
     std::vector<PassGraph> graphs;   // CUDA graphs of passes seen before (run_pass)
     std::vector<PassArgs> seen;
     unsigned long long graph_clock = 0;
@@ -136,7 +136,7 @@ struct DeviceCtx {
     std::vector<DevBuf *> scratch() {
         return {&digits, &vals, &start, &cnt, &ord, &buckets,
                 &lvlR[0], &lvlR[1], &lvlC[0], &lvlC[1], &hvy_hdr, &hvy_buckets, &hvy_tasks, &hvy_partials, &treeS[0],
-                &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum, &ba_prefix, &ba_T, &ba_prefix2, &ba_U, &ba_pts[0], &ba_pts[1]};
+                &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum, &ba_prefix, &ba_T, &ba_prefix2, &ba_U, &ba_pts[0], &ba_pts[1], &ba_pts[2]};
     }
     size_t scratch_bytes() {
         size_t s = 0;
@@ -145,7 +145,7 @@ struct DeviceCtx {
     }
     void release_all() {
         for (DevBuf *b : {&bases, &scalars, &digits, &vals, &start, &cnt, &ord, &buckets, &lvlR[0], &lvlR[1], &lvlC[0], &lvlC[1], &out, &hvy_hdr, &hvy_buckets,
-                          &hvy_tasks, &hvy_partials, &treeS[0], &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum, &chunk_partials, &norm_in, &norm_out, &tile_sums, &size_hist, &endo, &tbl_tmp, &ba_prefix, &ba_T, &ba_prefix2, &ba_U, &ba_pts[0], &ba_pts[1]})
+                          &hvy_tasks, &hvy_partials, &treeS[0], &treeS[1], &treeV[0], &treeV[1], &treeC[0], &treeC[1], &wsum, &chunk_partials, &norm_in, &norm_out, &tile_sums, &size_hist, &endo, &tbl_tmp, &ba_prefix, &ba_T, &ba_prefix2, &ba_U, &ba_pts[0], &ba_pts[1], &ba_pts[2]})
             b->release();
     }
 };
@@ -442,9 +442,13 @@ int pass_prepare(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v,
         if (int rc = cx.ba_T.reserve(t_el * FB)) return rc;
         if (int rc = cx.ba_prefix2.reserve(t_el * FB)) return rc;
         if (int rc = cx.ba_U.reserve(u_el * FB)) return rc;
-        if (int rc = cx.ba_pts[0].reserve(s1 * 2 * FB)) return rc;
-        if (R > 1)
-            if (int rc = cx.ba_pts[1].reserve((s1 + 1) / 2 * 2 * FB)) return rc;
+        // one output array per round (NOT a ping-pong pair: with the rounds running as two half-range pipelines on two
+        // streams, the pipeline that is a round ahead would overwrite what the other has not read yet)
+        size_t sr = s1;
+        for (int r = 0; r < R; r++) {
+            if (int rc = cx.ba_pts[r].reserve(sr * 2 * FB)) return rc;
+            sr = (sr + 1) / 2;
+        }
     }
     if (pa.finish) {
         uint32_t len = pl.nbw;
@@ -513,7 +517,7 @@ int pass_issue_main(DeviceCtx &cx, const PassArgs &pa, cudaStream_t st, bool pro
             CUDA_TRY(cudaStreamWaitEvent(cx.aux_stream, cx.ev_fork, 0));
         }
         for (int r = 0; r < pa.R; r++) {
-            uint32_t *out = cx.ba_pts[r & 1].as<uint32_t>();
+            uint32_t *out = cx.ba_pts[r].as<uint32_t>();
             const size_t s_part = split ? s_out / 2 + ((size_t)1 << (5 + pa.R)) + 1 : s_out;
             const BaPlan bp = ba_plan(s_part, cx.sm_count);
             for (int part = 0; part < (split ? 2 : 1); part++) {
