@@ -29,7 +29,7 @@ template <class F>
 __global__ void __launch_bounds__(128)
 k_accumulate(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ vals,
              const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, uint32_t nb,
-             uint32_t heavy_thr, const uint32_t *__restrict__ endo_x, uint32_t n_pts, int into,
+             uint32_t heavy_thr, const uint32_t *__restrict__ endo_x, uint32_t n_pts, int img_full, int into,
              uint32_t *__restrict__ buckets) {
     constexpr int W = field_words<F>::value;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -46,13 +46,14 @@ k_accumulate(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ va
     } else xyzz_set_inf(acc);
     uint32_t v = s < e ? vals[s] : 0;
     for (uint32_t j = s; j < e; j++) {
-        // index ≥ n_pts (GLV): the endomorphism image φ(P) = (β·x, y) of point index − n_pts, whose
-        // x comes from the precomputed β·x table
+        // index ≥ n_pts (GLV): an endomorphism image of point index − n_pts.  Two parts: φ(P) = (β·x, y), x from
+        // the precomputed β·x table, y from the base.  Four parts (img_full; G2): the full point from the image
+        // tables −ψ(Q), ψ²(Q), −ψ³(Q) stored back to back (index − n_pts runs over 3·n_pts entries).
         uint32_t idx = v & 0x7fffffffu;
         const bool endo = idx >= n_pts;
         if (endo) idx -= n_pts;
-        const uint32_t *p = bases + (size_t)idx * (2 * W);
-        const uint32_t *px = endo ? endo_x + (size_t)idx * W : p;
+        const uint32_t *p = (endo && img_full ? endo_x : bases) + (size_t)idx * (2 * W);
+        const uint32_t *px = endo && !img_full ? endo_x + (size_t)idx * W : p;
         const uint32_t sign = v >> 31;
         F x, y;
         f_load(x, px);
@@ -60,8 +61,9 @@ k_accumulate(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ va
         if (j + 1 < e) {  // pull the next point towards L1 while this one is being added
             v = vals[j + 1];
             uint32_t nidx = v & 0x7fffffffu;
-            if (nidx >= n_pts) nidx -= n_pts;
-            const char *q = reinterpret_cast<const char *>(bases + (size_t)nidx * (2 * W));
+            const bool nendo = nidx >= n_pts;
+            if (nendo) nidx -= n_pts;
+            const char *q = reinterpret_cast<const char *>((nendo && img_full ? endo_x : bases) + (size_t)nidx * (2 * W));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(q + 8 * W - 4));
         }
@@ -119,6 +121,55 @@ __device__ __forceinline__ void endo_mul(fp2 &r, const fp2 &x) {
     fp_mul(r.c0, x.c0, beta);
     fp_mul(r.c1, x.c1, beta);
 }
+// Four-part decomposition on G2 (gls4.cuh): the three image tables −ψ(Q), ψ²(Q), −ψ³(Q) of every base, full points,
+// stored back to back (n points each).  ψ(x, y) = (x̄·γx, ȳ·γy) with γx = (1+u)^−(p−1)/3 = (0, γx1) and
+// γy = (1+u)^−(p−1)/2; ψ²(x, y) = (β·x, −y).  The identity (all-zero) maps to itself.  Montgomery limbs; checked
+// against the big-int oracle (tests/test_glv_constants.py: constants, ψ(Q) = [z]·Q).
+__device__ __constant__ const uint32_t PSI_GX_C1[12] = {0x867545c3, 0x890dc9e4, 0x3285a5d5, 0x2af32253, 0x309b7e2c, 0x50880866,
+                                                        0x7e881024, 0xa20d1b8c, 0xe2db9068, 0x14e4f04f, 0x1564853a, 0x14e56d3f};
+__device__ __constant__ const uint32_t PSI_GY_C0[12] = {0xa55c9ad1, 0x3e2f585d, 0x86c18183, 0x4294213d, 0x8b623732, 0x382844c8,
+                                                        0x19103e18, 0x92ad2afd, 0xac7cf0b9, 0x1d794e4f, 0x7d825ec8, 0x0bd592fc};
+__device__ __constant__ const uint32_t PSI_GY_C1[12] = {0x5aa30fda, 0x7bcfa7a2, 0x2a927e7c, 0xdc17dec1, 0x6b4ebef1, 0x2f088dd8,
+                                                        0xda74d4a7, 0xd1ca2087, 0x96cebc1d, 0x2da25966, 0xbbfd87d2, 0x0e2b7eed};
+// (x̄·γx, ȳ·γy) of an Fp2 point, y negated when `neg_y`
+__device__ __forceinline__ void psi_apply(fp2 &rx, fp2 &ry, const fp2 &x, const fp2 &y, bool neg_y) {
+    fp g, t;
+    fp_load(g, PSI_GX_C1);
+    // (x0 − x1·u)·(γ·u) = x1·γ + x0·γ·u
+    fp_mul(t, x.c1, g);
+    fp_mul(rx.c1, x.c0, g);
+    rx.c0 = t;
+    fp2 gy, yc;
+    fp_load(gy.c0, PSI_GY_C0);
+    fp_load(gy.c1, PSI_GY_C1);
+    yc.c0 = y.c0;
+    fp_neg(yc.c1, y.c1);
+    fp2_mul(ry, yc, gy);
+    if (neg_y) { fp_neg(ry.c0, ry.c0); fp_neg(ry.c1, ry.c1); }
+}
+static __global__ void __launch_bounds__(128)
+k_psi_tables(const uint32_t *__restrict__ bases, size_t n, uint32_t *__restrict__ img) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp2 x, y, x1, y1, x2, y2, x3, y3;
+    f_load(x, bases + i * 48);
+    f_load(y, bases + i * 48 + 24);
+    psi_apply(x1, y1, x, y, true);                 // −ψ(Q)
+    fp beta;
+    fp_load(beta, GLV_BETA);
+    fp_mul(x2.c0, x.c0, beta);                     // ψ²(Q) = (β·x, −y)
+    fp_mul(x2.c1, x.c1, beta);
+    fp_neg(y2.c0, y.c0);
+    fp_neg(y2.c1, y.c1);
+    psi_apply(x3, y3, x2, y2, true);               // −ψ³(Q) = −ψ(ψ²(Q))
+    f_store(img + i * 48, x1);
+    f_store(img + i * 48 + 24, y1);
+    f_store(img + (n + i) * 48, x2);
+    f_store(img + (n + i) * 48 + 24, y2);
+    f_store(img + (2 * n + i) * 48, x3);
+    f_store(img + (2 * n + i) * 48 + 24, y3);
+}
+
 template <class F>
 static __global__ void __launch_bounds__(256)
 k_endo_table(const uint32_t *__restrict__ bases, size_t n, uint32_t *__restrict__ endo_x) {
@@ -173,7 +224,7 @@ template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_heavy_tasks(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ vals,
               const HeavyHeader *__restrict__ hdr, const HeavyTask *__restrict__ tasks, const uint32_t *__restrict__ endo_x,
-              uint32_t n_pts, uint32_t *__restrict__ partials) {
+              uint32_t n_pts, int img_full, uint32_t *__restrict__ partials) {
     constexpr int W = field_words<F>::value;
     constexpr int PW = 4 * W;
     __shared__ __align__(16) uint32_t smem[(THREADS / 2) * PW];
@@ -196,9 +247,9 @@ k_heavy_tasks(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ v
             uint32_t idx = v & 0x7fffffffu;
             const bool endo = idx >= n_pts;
             if (endo) idx -= n_pts;
-            const uint32_t *p = bases + (size_t)idx * (2 * W);
+            const uint32_t *p = (endo && img_full ? endo_x : bases) + (size_t)idx * (2 * W);
             F x, y;
-            f_load(x, endo ? endo_x + (size_t)idx * W : p);
+            f_load(x, endo && !img_full ? endo_x + (size_t)idx * W : p);
             f_load(y, p + W);
             if (f_is_zero(x) && f_is_zero(y)) continue;
             f_cneg(y, y, v >> 31);

@@ -82,7 +82,7 @@ struct PassArgs {
     const uint32_t *d_bases = nullptr, *d_scalars = nullptr;
     uint32_t *d_out = nullptr;
     size_t n = 0;
-    int c = 0, nwin = 0, glv = 0;          // plan; glv: 0 off, 1 on, 2 on with the unsigned top digit
+    int c = 0, nwin = 0, glv = 0;          // plan; glv: 0 off; 1 / 2 two parts (φ) with a carry window / unsigned top digit; 3 / 4 four parts (ψ, G2)
     uint32_t nbw = 0, nb = 0;
     const void *tbl_p = nullptr;           // fixed-base table (or null)
     size_t tbl_stride = 0;
@@ -156,13 +156,13 @@ struct DeviceCtx {
 struct Tun {
     int window_override = 0;
     size_t max_chunk_override = 0;
-    int glv_mode = -1;  // -1 automatic (time model; default), 0 never, 1 always
+    int glv_mode = -1;  // -1 automatic (time model; default), 0 never, 1 two parts (φ), 2 four parts on G2 (ψ; G1: two)
     bool profiling = false;
     int stream_slices = 8;          // (at most) host-buffer MSMs of ≥ stream_min points per device are uploaded and accumulated in slices
     size_t stream_min = 1u << 18;
     int heavy_factor = 0;  // a bucket is heavy above heavy_factor × the mean occupancy (see run_pass); 0 = automatic
     int batch_affine = -1; // -1 automatic, 0 never, 1..3 = pairwise batched-affine rounds before the XYZZ accumulation
-    bool graphs = true;    // record a pass seen twice as CUDA graphs and replay it
+    bool graphs = !(getenv("B200MSM_GRAPHS") && atoi(getenv("B200MSM_GRAPHS")) == 0);   // record a pass seen twice as CUDA graphs and replay it (env: debugging)
     unsigned epoch = 0;    // bumped by every setter that changes what a pass allocates (fit caches are keyed on it)
 };
 struct Share;
@@ -381,14 +381,15 @@ int pass_prepare(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v,
         pl.c = tbl->c;
         pl.nwin = tbl->nwin;
         pl.glv = pl.split = false;
+        pl.parts = 1;
         pl.nbw = 1u << (pl.c - 1);
         pl.nb = pl.nbw;                       // one bucket set shared by all windows
     } else auto_plan(n, g2, tn.glv_mode, tn.window_override, pl, tn.batch_affine);
     if (tbl) { pa.d_bases = (const uint32_t *)tbl->p; pa.tbl_p = tbl->p; pa.tbl_stride = tbl->stride; }
-    pa.c = pl.c; pa.nwin = pl.nwin; pa.glv = pl.glv ? (pl.split ? 2 : 1) : 0; pa.nbw = pl.nbw; pa.nb = pl.nb;
+    pa.c = pl.c; pa.nwin = pl.nwin; pa.glv = pl.glv ? (pl.parts == 4 ? 3 : 1) + (pl.split ? 1 : 0) : 0; pa.nbw = pl.nbw; pa.nb = pl.nb;
     const int rwin = tbl ? 1 : pl.nwin;       // windows the reduction sees
     cx.last_plan[0] = pl.c; cx.last_plan[1] = pl.nwin; cx.last_plan[2] = pa.glv; cx.last_plan[3] = tbl ? 1 : 0;
-    const size_t entries = pl.glv ? 2 * n : n;  // per window
+    const size_t entries = (size_t)pl.parts * n;  // per window
     const size_t m = entries * (size_t)pl.nwin;
     // heavy buckets: one thread per bucket is the efficient shape (≈0.31 product-times per entry
     // per warp vs ≈1 for the block-cooperative path), so a bucket only counts as heavy when its
@@ -429,8 +430,8 @@ int pass_prepare(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v,
     if (int rc = cx.hvy_partials.reserve(max_tasks * PB)) return rc;
     if (int rc = cx.tile_sums.reserve(((size_t)pl.nb / 2048 + 4) * 4)) return rc;
     if (int rc = cx.size_hist.reserve(2 * 4096 * 4)) return rc;
-    if (pl.glv)
-        if (int rc = cx.endo.reserve(n * (size_t)W * 4)) return rc;
+    if (pl.glv)   // β·x table (two parts), or the three full-point image tables −ψ, ψ², −ψ³ (four parts, G2)
+        if (int rc = cx.endo.reserve(n * (size_t)W * 4 * (pl.parts == 4 ? 6 : 1))) return rc;
     if (R > 0) {
         const size_t FB = (size_t)W * 4, s1 = (slots_max + 1) / 2;
         // round 1 is the largest; it may run unsplit or as two half-range pipelines (pass_issue_main), whose plans
@@ -493,8 +494,10 @@ int pass_issue_main(DeviceCtx &cx, const PassArgs &pa, cudaStream_t st, bool pro
     uint32_t *vals = cx.vals.as<uint32_t>(), *ord = cx.ord.as<uint32_t>(), *start = cx.start.as<uint32_t>();
     const uint32_t *endo_x = nullptr;
     uint32_t n_pts = 0xffffffffu;
-    if (pa.glv) {  // β·x table for the endomorphism images (one product per base)
-        (g2 ? launch_endo_table_g2 : launch_endo_table_g1)(pa.d_bases, pa.n, cx.endo.as<uint32_t>(), st);
+    const int parts = pa.glv == 0 ? 1 : (pa.glv <= 2 ? 2 : 4), img_full = parts == 4;
+    if (pa.glv) {  // β·x table for the endomorphism images (one product per base), or the three ψ image tables
+        if (img_full) launch_psi_tables_g2(pa.d_bases, pa.n, cx.endo.as<uint32_t>(), st);
+        else (g2 ? launch_endo_table_g2 : launch_endo_table_g1)(pa.d_bases, pa.n, cx.endo.as<uint32_t>(), st);
         endo_x = cx.endo.as<uint32_t>();
         n_pts = (uint32_t)pa.n;
     }
@@ -502,7 +505,7 @@ int pass_issue_main(DeviceCtx &cx, const PassArgs &pa, cudaStream_t st, bool pro
     //     additions that share one inversion per ≈10^5 pairs; what is left is accumulated in XYZZ form below
     const uint32_t *acc_pts = pa.d_bases, *acc_vals = vals;
     if (pa.R > 0) {
-        const size_t entries = pa.glv ? 2 * pa.n : pa.n, m = entries * (size_t)pa.nwin;
+        const size_t entries = (size_t)parts * pa.n, m = entries * (size_t)pa.nwin;
         size_t s_out = (m + (size_t)pa.nb * ((1u << pa.R) - 1) + 1) / 2;
         const uint32_t *src = pa.d_bases;
         // Large rounds run as TWO interleaved pipelines over the two halves of the slot range, on two streams: the
@@ -516,16 +519,18 @@ int pass_issue_main(DeviceCtx &cx, const PassArgs &pa, cudaStream_t st, bool pro
             CUDA_TRY(cudaEventRecord(cx.ev_fork, st));
             CUDA_TRY(cudaStreamWaitEvent(cx.aux_stream, cx.ev_fork, 0));
         }
+        size_t o1 = 0, o2 = 0, o3 = 0;   // part 1's scratch: fixed offsets (the first round's sizes) for ALL rounds — the pipelines may be a
+                                         // round apart, and offsets that shrank with the round would put part 1's round r+1 on top of part 0's round r
         for (int r = 0; r < pa.R; r++) {
             uint32_t *out = cx.ba_pts[r].as<uint32_t>();
             const size_t s_part = split ? s_out / 2 + ((size_t)1 << (5 + pa.R)) + 1 : s_out;
             const BaPlan bp = ba_plan(s_part, cx.sm_count);
+            if (r == 0) { o1 = (size_t)bp.NT * bp.K; o2 = bp.NT; o3 = bp.NU; }
             for (int part = 0; part < (split ? 2 : 1); part++) {
-                const size_t o1 = part ? (size_t)bp.NT * bp.K : 0, o2 = part ? bp.NT : 0, o3 = part ? bp.NU : 0;
                 (g2 ? launch_ba_round_g2 : launch_ba_round_g1)(r == 0, src, vals, endo_x, n_pts, start + pa.nb, r, bp,
-                                                               cx.ba_prefix.as<uint32_t>() + o1 * FW, cx.ba_T.as<uint32_t>() + o2 * FW,
-                                                               cx.ba_prefix2.as<uint32_t>() + o2 * FW, cx.ba_U.as<uint32_t>() + o3 * FW, out,
-                                                               part ? cx.aux_stream : st, part, align_log);
+                                                               cx.ba_prefix.as<uint32_t>() + (part ? o1 : 0) * FW, cx.ba_T.as<uint32_t>() + (part ? o2 : 0) * FW,
+                                                               cx.ba_prefix2.as<uint32_t>() + (part ? o2 : 0) * FW, cx.ba_U.as<uint32_t>() + (part ? o3 : 0) * FW, out,
+                                                               part ? cx.aux_stream : st, part, align_log, img_full);
             }
             src = out;
             s_out = (s_out + 1) / 2;
@@ -543,14 +548,14 @@ int pass_issue_main(DeviceCtx &cx, const PassArgs &pa, cudaStream_t st, bool pro
     CUDA_TRY(cudaStreamWaitEvent(cx.aux_stream, cx.ev_fork, 0));
     (g2 ? launch_heavy_g2 : launch_heavy_g1)(acc_pts, acc_vals, start, ord, pa.nb, pa.heavy_thr, endo_x, n_pts, cx.hvy_hdr.p,
                                              cx.hvy_buckets.p, cx.hvy_tasks.p, cx.hvy_partials.as<uint32_t>(), pa.into,
-                                             cx.buckets.as<uint32_t>(), cx.sm_count * 4, cx.aux_stream, pa.R);
+                                             cx.buckets.as<uint32_t>(), cx.sm_count * 4, cx.aux_stream, pa.R, img_full);
     CUDA_TRY(cudaEventRecord(cx.ev_join, cx.aux_stream));
     if (pa.R > 0)
         (g2 ? launch_accumulate_direct_g2 : launch_accumulate_direct_g1)(acc_pts, start, ord, pa.nb, pa.heavy_thr, pa.R, pa.into,
                                                                          cx.buckets.as<uint32_t>(), st);
     else
         (g2 ? launch_accumulate_g2 : launch_accumulate_g1)(pa.d_bases, vals, start, ord, pa.nb, pa.heavy_thr, endo_x, n_pts, pa.into,
-                                                           cx.buckets.as<uint32_t>(), st);
+                                                           cx.buckets.as<uint32_t>(), st, img_full);
     CUDA_TRY(cudaStreamWaitEvent(st, cx.ev_join, 0));
     mark();
     if (!pa.finish) {
@@ -602,7 +607,7 @@ int pass_issue_main(DeviceCtx &cx, const PassArgs &pa, cudaStream_t st, bool pro
     mark();
     // 6. window values and Horner over the windows → one Jacobian point
     (g2 ? launch_combine_g2 : launch_combine_g1)(Sin, cx.treeV[cur].as<uint32_t>(), Cin ? Ccur : nullptr, tstride, logS, log2M,
-                                                 rwin, pa.c, pa.glv == 2 ? 1 : 0, cx.wsum.as<uint32_t>(), pa.d_out, st);
+                                                 rwin, pa.c, ((pa.glv == 2 || pa.glv == 4) ? 1 : 0) | (getenv("B200MSM_TOP_ASIDE") && atoi(getenv("B200MSM_TOP_ASIDE")) == 0 ? 2 : 0), cx.wsum.as<uint32_t>(), pa.d_out, st);
     mark();
     if (st != caller_st) {
         CUDA_TRY(cudaEventRecord(cx.ev_tail_join, st));
@@ -716,7 +721,7 @@ size_t pass_scratch_bytes(size_t n, bool g2, int c_override, bool table = false)
     c = std::max(2, std::min(c, 22));
     size_t nwin = (256 + c - 1) / c, nb = nwin << (c - 1), m = n * nwin;  // the GLV plan needs about the same
     size_t PB = g2 ? 384 : 192;
-    const size_t ba = m * (PB * 3 / 8) + nb * 16;   // batched-affine rounds: prefix products + the first round's output (upper bound)
+    const size_t ba = m * (PB * 9 / 16) + nb * 16;  // batched-affine rounds: prefix products (m/2 elements) + one output array per round (m/2 + m/4 + m/8 points)
     if (table) return m * 8 + (nb / nwin) * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + ba + (64u << 20);
     return m * 8 + nb * (PB + PB / 8 + 20) + m / 96 * (PB + 20) + n * (PB / 4) + ba + (64u << 20);
 }
@@ -752,7 +757,7 @@ int run_group(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases, cons
         if (tbl) return cn * tbl->nwin + ((size_t)7 << (tbl->c - 1)) >= 0xfff00000ull || pass_scratch_bytes(cn, g2, tbl->c, true) > budget;
         Plan p;
         auto_plan(cn, g2, tn.glv_mode, tn.window_override, p, tn.batch_affine);
-        size_t ent = (p.glv ? 2 : 1) * cn;
+        size_t ent = (size_t)p.parts * cn;
         return ent * p.nwin + (size_t)p.nb * 7 >= 0xfff00000ull || cn >= (1ull << 30) || pass_scratch_bytes(cn, g2, tn.window_override) > budget;
     };
     while (too_big((n + chunks - 1) / chunks)) {
@@ -1464,7 +1469,7 @@ int b200msm_set_heavy_factor(int f) {
     return 0;
 }
 int b200msm_set_glv(int mode) {
-    if (mode < -1 || mode > 1) return fail(B200MSM_EINVAL, "glv mode must be -1 (auto), 0 (off) or 1 (on)");
+    if (mode < -1 || mode > 2) return fail(B200MSM_EINVAL, "glv mode must be -1 (auto), 0 (off), 1 (two parts) or 2 (four parts on G2)");
     tun_update([&](Tun &t) { t.glv_mode = mode; });
     return 0;
 }
@@ -1487,12 +1492,12 @@ int b200msm_set_profiling(int on) {
 }
 int b200msm_plan_query(int group, size_t n, int glv_mode, int out[4]) {
     if (group != B200MSM_G1 && group != B200MSM_G2) return fail(B200MSM_EINVAL, "bad group");
-    if (!out || n == 0 || glv_mode < -1 || glv_mode > 1) return fail(B200MSM_EINVAL, "bad argument");
+    if (!out || n == 0 || glv_mode < -1 || glv_mode > 2) return fail(B200MSM_EINVAL, "bad argument");
     Plan pl;
     auto_plan(n, group == B200MSM_G2, glv_mode, 0, pl, tun_snapshot().batch_affine);   // host arithmetic only: no device needed
     out[0] = pl.c;
     out[1] = pl.nwin;
-    out[2] = pl.glv ? (pl.split ? 2 : 1) : 0;
+    out[2] = pl.glv ? (pl.parts == 4 ? 3 : 1) + (pl.split ? 1 : 0) : 0;
     out[3] = (int)std::min<uint64_t>(pl.nb, 0x7fffffff);
     return 0;
 }

@@ -74,8 +74,9 @@ template <class F> __device__ __forceinline__ bool f_eq(const F &a, const F &b) 
 struct BaSrc {
     const uint32_t *pts;     // first round: the bases (or the fixed-base table); later: the previous round's output
     const uint32_t *vals;    // first round: sorted entries (point index | sign ≪ 31; 0xffffffff = padding)
-    const uint32_t *endo_x;  // first round, GLV: β·x table for the entries with index ≥ n_pts
+    const uint32_t *endo_x;  // first round, GLV: β·x table for the entries with index ≥ n_pts …
     uint32_t n_pts;
+    int img_full;            // … or (four parts, G2) the full-point image tables −ψ, ψ², −ψ³ back to back (accumulate.cuh)
 };
 
 // x of input position `pos`; false when the position holds nothing.  FIRST: `v` returns the entry
@@ -89,8 +90,8 @@ __device__ __forceinline__ bool ba_load_x(const BaSrc &s, size_t pos, F &x, uint
         uint32_t idx = v & 0x7fffffffu;
         const bool endo = idx >= s.n_pts;
         if (endo) idx -= s.n_pts;
-        const uint32_t *p = s.pts + (size_t)idx * (2 * W);
-        f_load(x, endo ? s.endo_x + (size_t)idx * W : p);
+        const uint32_t *p = (endo && s.img_full ? s.endo_x : s.pts) + (size_t)idx * (2 * W);
+        f_load(x, endo && !s.img_full ? s.endo_x + (size_t)idx * W : p);
         if (f_is_zero(x)) {                       // x = 0: the identity encoding iff y = 0 too (rare either way)
             F y;
             f_load(y, p + W);
@@ -106,8 +107,9 @@ __device__ __forceinline__ void ba_load_y(const BaSrc &s, size_t pos, uint32_t v
     constexpr int W = field_words<F>::value;
     if (FIRST) {
         uint32_t idx = v & 0x7fffffffu;
-        if (idx >= s.n_pts) idx -= s.n_pts;
-        f_load(y, s.pts + (size_t)idx * (2 * W) + W);
+        const bool endo = idx >= s.n_pts;
+        if (endo) idx -= s.n_pts;
+        f_load(y, (endo && s.img_full ? s.endo_x : s.pts) + (size_t)idx * (2 * W) + W);
         f_cneg(y, y, v >> 31);
     } else f_load(y, s.pts + pos * (2 * W) + W);
 }

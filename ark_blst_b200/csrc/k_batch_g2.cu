@@ -5,9 +5,9 @@
 namespace b200msm {
 void launch_ba_round_g2(int first, const uint32_t *src, const uint32_t *vals, const uint32_t *endo_x, uint32_t n_pts,
                         const uint32_t *total_ptr, int round, const BaPlan &bp, uint32_t *prefix, uint32_t *T, uint32_t *prefix2,
-                        uint32_t *U, uint32_t *out, cudaStream_t st, int part, int split_align_log) {
+                        uint32_t *U, uint32_t *out, cudaStream_t st, int part, int split_align_log, int img_full) {
     for (int k = 0; k < 5; k++) count_launch();
-    BaSrc s{src, vals, endo_x, n_pts};
+    BaSrc s{src, vals, endo_x, n_pts, img_full};
     const int shift = round + 1;
     const unsigned blocks = blocks_for(bp.NT, 128);
     if (first) k_ba_fwd<fp2, true><<<blocks, 128, 0, st>>>(s, total_ptr, shift, part, split_align_log, bp.NT, bp.K, prefix, T);

@@ -3,6 +3,7 @@
 // runs on the MSM path) and the ordering of the buckets by size.
 
 #include "launch.h"
+#include "gls4.cuh"
 #include "scalar.cuh"
 
 namespace b200msm {
@@ -25,28 +26,39 @@ __global__ void k_digits_dbg(const uint32_t *__restrict__ scalars, size_t n, int
 // yields the bucket offsets.
 // `glv` (G1 only): every scalar is split into (k1, k2) with k = k1 + k2·λ; entry i of a window is
 // k1's digit for point i, entry n + i is k2's digit for the endomorphism image φ(P_i).
+// glv: 0 none; 1 / 2 two parts (k = k1 + k2·λ over P, φ(P)) with a carry window / with the unsigned top digit;
+// 3 / 4 four parts (G2: base-|z| digits over Q, −ψ(Q), ψ²(Q), −ψ³(Q), gls4.cuh) with a carry window / unsigned top digit.
+// Entry part·n + i of a window is part `part`'s digit for point i.
 __global__ void __launch_bounds__(256)
 k_hist(const uint32_t *__restrict__ scalars, size_t n, int mont, int glv, int c, int nwin, int shared_buckets,
        uint32_t *__restrict__ dig, uint32_t *__restrict__ count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t s[8], s2[8];
-    load_scalar(s, scalars, i, mont);
-    if (glv) {
+    uint32_t s[4][8];
+    load_scalar(s[0], scalars, i, mont);
+    const int parts = glv == 0 ? 1 : (glv <= 2 ? 2 : 4);
+    if (parts == 2) {
         uint32_t k[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) k[j] = s[j];
-        glv_decompose(k, s, s2);
+        for (int j = 0; j < 8; j++) k[j] = s[0][j];
+        glv_decompose(k, s[0], s[1]);
+    } else if (parts == 4) {
+        uint32_t k[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) k[j] = s[0][j];
+        gls4_decompose(k, s);
     }
     const uint32_t nbw = 1u << (c - 1);
-    const size_t per_window = glv ? 2 * n : n;
-    // glv == 2 (c divides 128): the top c bits of a 128-bit half are taken UNSIGNED, so no carry
+    const size_t per_window = (size_t)parts * n;
+    // split (c divides the parts' width): the top c bits of a part are taken UNSIGNED, so no carry
     // window follows them; their digit u ∈ [0, 2^c] goes to window nwin−2 when u ≤ 2^(c−1) and, as
     // u − 2^(c−1), to window nwin−1 otherwise (k_combine adds 2^(c−1)·Σ buckets for that window
     // and gives both the weight of window nwin−2)
-    const int split = glv == 2;
-    for (int half = 0; half <= (glv ? 1 : 0); half++) {
-        const uint32_t *sc = half ? s2 : s;
+    const int split = glv == 2 || glv == 4;
+#pragma unroll
+    for (int part = 0; part < 4; part++) {         // (unrolled: s[part] stays in registers)
+        if (part >= parts) break;
+        const uint32_t *sc = s[part];
         uint32_t utop = 0;
         if (split) utop = scalar_bits(sc, (nwin - 2) * c - 1, c + 1), utop = (utop >> 1) + (utop & 1);
         for (int w = 0; w < nwin; w++) {
@@ -57,7 +69,7 @@ k_hist(const uint32_t *__restrict__ scalars, size_t n, int mont, int glv, int c,
             } else d = booth_digit(sc, w, c);
             uint32_t neg = d < 0;
             uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
-            dig[(size_t)w * per_window + (half ? n : 0) + i] = (mag << 1) | neg;   // window-major; 0 = zero digit
+            dig[(size_t)w * per_window + (size_t)part * n + i] = (mag << 1) | neg;   // window-major; 0 = zero digit
             if (mag) atomicAdd(&count[(shared_buckets ? 0u : (uint32_t)w * nbw) + (mag - 1)], 1u);
         }
     }
@@ -210,7 +222,8 @@ void launch_group_by_bucket(const uint32_t *scalars, size_t n, int mont, int glv
                             size_t tbl_stride, int pad_log) {
     for (int k = 0; k < 7; k++) count_launch();
     const uint32_t pad_mask = (1u << pad_log) - 1;
-    if (pad_log) cudaMemsetAsync(vals, 0xff, ((glv ? 2 * n : n) * (size_t)nwin + (size_t)nb * pad_mask) * 4, st);
+    const size_t parts = glv == 0 ? 1 : (glv <= 2 ? 2 : 4);
+    if (pad_log) cudaMemsetAsync(vals, 0xff, (parts * n * (size_t)nwin + (size_t)nb * pad_mask) * 4, st);
     cudaMemsetAsync(count, 0, (size_t)nb * 4, st);
     k_hist<<<blocks_for(n, 256), 256, 0, st>>>(scalars, n, mont, glv, c, nwin, tbl_stride ? 1 : 0, dig, count);
     size_t ntiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
@@ -218,7 +231,7 @@ void launch_group_by_bucket(const uint32_t *scalars, size_t n, int mont, int glv
     k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, ntiles, tile_sums + ntiles);
     k_scan_add<<<blocks_for(nb, 256), 256, 0, st>>>(start, nb, tile_sums, tile_sums + ntiles);
     cudaMemsetAsync(count, 0, (size_t)nb * 4, st);   // reused as the scatter cursors
-    const size_t entries = glv ? 2 * n : n;  // per window
+    const size_t entries = parts * n;  // per window
     k_scatter<<<dim3(blocks_for(entries, 256), (unsigned)nwin), 256, 0, st>>>(dig, entries, c, tbl_stride, start, count, vals);
 }
 // hist: 2·SIZE_BINS u32 of scratch

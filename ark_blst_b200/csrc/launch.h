@@ -12,7 +12,8 @@ namespace b200msm {
 void launch_digits_dbg(const uint32_t *scalars, size_t n, int mont, int c, int nwin, int *out, cudaStream_t st);
 // hand-written grouping by bucket (counting sort on the bucket id, built from the scalars):
 // glv: 1 = split every scalar in two 128-bit halves (entries per window double), 2 = the same with the top c bits taken
-// unsigned and spread over the last two windows (c | 128, nwin = 128/c + 1; see k_hist); dig: entries·nwin u32, count: nb u32, start: nb+2 u32, tile_sums: nb/2048+2 u32, vals: ≥ n·nwin u32
+// unsigned and spread over the last two windows (c | 128, nwin = 128/c + 1; see k_hist); 3 / 4 = four 64-bit parts (G2,
+// gls4.cuh) with a carry window / with the unsigned top digit (entries per window ×4); dig: entries·nwin u32, count: nb u32, start: nb+2 u32, tile_sums: nb/2048+2 u32, vals: ≥ n·nwin u32
 // tbl_stride > 0 (fixed-base window table, `tbl_stride` points per window): all windows share one bucket set — nb = 2^(c−1),
 // entries are grouped by the digit alone and carry the table index w·tbl_stride + i (must stay below 2^31)
 // pad_log > 0 (batched-affine rounds follow): every bucket's segment is padded to a multiple of 2^pad_log entries and
@@ -28,19 +29,22 @@ constexpr uint32_t HEAVY_CHUNK = 4096;  // entries per block task of a heavy buc
 // the β·x table; pass nullptr / 0xffffffff when unused
 void launch_accumulate_g1(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
                           uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, int into, uint32_t *buckets,
-                          cudaStream_t st);
+                          cudaStream_t st, int img_full = 0);
 void launch_accumulate_g2(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
                           uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, int into, uint32_t *buckets,
-                          cudaStream_t st);
+                          cudaStream_t st, int img_full = 0);
 void launch_endo_table_g1(const uint32_t *bases, size_t n, uint32_t *endo_x, cudaStream_t st);
 void launch_endo_table_g2(const uint32_t *bases, size_t n, uint32_t *endo_x, cudaStream_t st);
+// G2, four-part decomposition: img ← the image tables −ψ(Q), ψ²(Q), −ψ³(Q) (3·n full points); kernels then take img as
+// `endo_x` with img_full = 1 (value indices n_pts + j·n_pts + i name image j+1 of point i)
+void launch_psi_tables_g2(const uint32_t *bases, size_t n, uint32_t *img, cudaStream_t st);
 // plan + block tasks + per-bucket fold for buckets above heavy_thr; hdr must be zeroed (8 bytes)
 void launch_heavy_g1(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
                      uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, void *hdr, void *hb, void *tasks,
-                     uint32_t *partials, int into, uint32_t *buckets, int grid, cudaStream_t st, int shift = 0);
+                     uint32_t *partials, int into, uint32_t *buckets, int grid, cudaStream_t st, int shift = 0, int img_full = 0);
 void launch_heavy_g2(const uint32_t *bases, const uint32_t *vals, const uint32_t *start, const uint32_t *order,
                      uint32_t nb, uint32_t heavy_thr, const uint32_t *endo_x, uint32_t n_pts, void *hdr, void *hb, void *tasks,
-                     uint32_t *partials, int into, uint32_t *buckets, int grid, cudaStream_t st, int shift = 0);
+                     uint32_t *partials, int into, uint32_t *buckets, int grid, cudaStream_t st, int shift = 0, int img_full = 0);
 // (vals == nullptr with shift = R: direct mode over the array the batched-affine rounds left, see k_batch_g{1,2}.cu)
 
 // k_batch_g{1,2}.cu — batched-affine pairing rounds (batch_affine.cuh).  One round halves the (padded) entry array:
@@ -53,10 +57,10 @@ struct BaPlan { uint32_t NT, K, NU, K2; };
 BaPlan ba_plan(size_t s_out_max, int sm_count);
 void launch_ba_round_g1(int first, const uint32_t *src, const uint32_t *vals, const uint32_t *endo_x, uint32_t n_pts,
                         const uint32_t *total_ptr, int round, const BaPlan &bp, uint32_t *prefix, uint32_t *T, uint32_t *prefix2,
-                        uint32_t *U, uint32_t *out, cudaStream_t st, int part = 0, int split_align_log = 0);
+                        uint32_t *U, uint32_t *out, cudaStream_t st, int part = 0, int split_align_log = 0, int img_full = 0);
 void launch_ba_round_g2(int first, const uint32_t *src, const uint32_t *vals, const uint32_t *endo_x, uint32_t n_pts,
                         const uint32_t *total_ptr, int round, const BaPlan &bp, uint32_t *prefix, uint32_t *T, uint32_t *prefix2,
-                        uint32_t *U, uint32_t *out, cudaStream_t st, int part = 0, int split_align_log = 0);
+                        uint32_t *U, uint32_t *out, cudaStream_t st, int part = 0, int split_align_log = 0, int img_full = 0);
 void launch_accumulate_direct_g1(const uint32_t *pts, const uint32_t *start, const uint32_t *order, uint32_t nb, uint32_t heavy_thr,
                                  int shift, int into, uint32_t *buckets, cudaStream_t st);
 void launch_accumulate_direct_g2(const uint32_t *pts, const uint32_t *start, const uint32_t *order, uint32_t nb, uint32_t heavy_thr,

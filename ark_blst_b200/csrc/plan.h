@@ -12,19 +12,22 @@ namespace b200msm {
 
 struct Plan {
     int c = 0, nwin = 0;
-    bool glv = false;          // split every scalar into two 128-bit halves (k1 + k2·λ) over P and φ(P) = (β·x, y)
-    bool split = false;        // GLV with c | 128: unsigned top digit spread over the last two windows (k_hist)
+    bool glv = false;          // split every scalar into two 128-bit halves (k1 + k2·λ) over P and φ(P) = (β·x, y) …
+    int parts = 1;             // … or, on G2, into four 64-bit digits base |z| over Q, −ψ(Q), ψ²(Q), −ψ³(Q) (gls4.cuh): 1 / 2 / 4
+    bool split = false;        // GLV with c | part bits: unsigned top digit spread over the last two windows (k_hist)
     uint32_t nbw = 0, nb = 0;  // buckets per window, total
 };
 
-// Windows of a plan. Plain: c·W ≥ 256 so the top Booth carry stays inside. GLV halves are below
-// 2^128: when c divides 128 their top c bits are taken unsigned (digit ≤ 2^c → two windows' worth
-// of buckets, no carry window); otherwise c·W ≥ 129 as for the plain plan.
-inline int plan_windows(bool glv, int c, bool *split) {
-    *split = glv && 128 % c == 0;
-    if (!glv) return (256 + c - 1) / c;
-    return *split ? 128 / c + 1 : (129 + c - 1) / c;
+// Windows of a plan. Plain: c·W ≥ 256 so the top Booth carry stays inside. The parts of a decomposed
+// scalar are below 2^128 (two) or 2^64 (four): when c divides that width their top c bits are taken
+// unsigned (digit ≤ 2^c → two windows' worth of buckets, no carry window); otherwise c·W ≥ width + 1.
+inline int plan_windows(int parts, int c, bool *split) {
+    const int bits = 256 / parts;
+    *split = parts > 1 && bits % c == 0;
+    if (parts == 1) return (256 + c - 1) / c;
+    return *split ? bits / c + 1 : (bits + 1 + c - 1) / c;
 }
+inline int plan_windows(bool glv, int c, bool *split) { return plan_windows(glv ? 2 : 1, c, split); }
 
 // Window width and GLV choice from a time model fitted to the measured phases on B200 (µs):
 // accumulation at 88 % (G1) / 76 % (G2) of the 18.5 T IMAD/s pipe, the fan-in-32 reduction level
@@ -42,47 +45,53 @@ inline double ba_time_factor(double avg_occupancy, bool g2, int ba_mode) {
     if (R == 1) return 0.93;
     return g2 ? 0.75 : 0.79;
 }
-inline double plan_time_us(size_t n, bool g2, bool glv, int c, int ba_mode = -1) {
+inline double plan_time_us(size_t n, bool g2, int parts, int c, int ba_mode = -1) {
     bool split;
-    const double W = plan_windows(glv, c, &split), entries = (glv ? 2.0 : 1.0) * (double)n;
+    const bool glv = parts > 1;
+    const double W = plan_windows(parts, c, &split), entries = (double)parts * (double)n;
     const double Wacc = split ? W - 1 : W;  // an entry lands in one of the two top windows
     const double madd = g2 ? 28 : 10, add = g2 ? 40 : 14, pipe = 18.5e6;  // IMAD per µs
     // one thread per bucket: below ≈2.5 warps per scheduler (4 × 148 of them) the dependent-issue latency of the
     // product chain shows (measured with 2^15 buckets: 0.6 of the pipe)
     // (GLV: the φ(P) entries read x from the β·x table and y from the base record — measured 2.5 % / 6 % slower)
     const double wps = W * std::pow(2.0, c - 1) / 32 / 592;
-    const double eff = std::min(g2 ? 0.76 : 0.88, 0.35 * wps) * (glv ? (g2 ? 0.94 : 0.975) : 1.0);
+    // (four parts on G2: the images come from three full-point tables, 768 B of gather per base instead of 288)
+    const double eff = std::min(g2 ? 0.76 : 0.88, 0.35 * wps) * (glv ? (g2 ? (parts == 4 ? 0.91 : 0.94) : 0.975) : 1.0);
     double t = entries * Wacc * madd * 588 / (pipe * eff) * ba_time_factor(entries / std::pow(2.0, c - 1), g2, ba_mode);
     t += W * std::pow(2.0, c - 1) * 2 * add * 588 / (pipe * 0.55);
     t += (split ? (W - 2) * c + c - 1 : (W - 1) * c) * (g2 ? 11.0 : 3.4) + 250;
     t += entries * W * 2.3e-5;
     if (glv) {
-        t += (double)n * (g2 ? 2 : 1) * 588 / (pipe * 0.5) + (double)n * 4e-5;  // β·x table, decomposition
+        t += (double)n * (parts == 4 ? 12 : (g2 ? 2 : 1)) * 588 / (pipe * 0.5) + (double)n * (parts == 4 ? 1.2e-4 : 4e-5);  // image table(s), decomposition
         // a top window with few bits piles its entries into few buckets: block-cooperative path, ≈3.5× the cost
         // The halves are below λ ≈ 0.673·2^128, so the top window only uses ⌊λ / 2^(c(W−1))⌋ + 1 of its buckets.
         // When that is few, its entries pile up past the heavy-bucket threshold and go down the block-cooperative
         // path (and serialise the grouping's atomics): never pick such a width.
+        // (four parts: digits below |z| ≈ 0.82·2^64)
         const int shift = c * ((int)W - 1);
-        const double top_buckets = std::floor(0.673 * std::pow(2.0, 128 - shift)) + 1;
+        const double top_buckets = std::floor((parts == 4 ? 0.82 : 0.673) * std::pow(2.0, 256 / parts - shift)) + 1;
         const double thr = std::max(std::max(32.0, 3 * entries / std::pow(2.0, c - 1)), entries * W / 175000);
         if (!split && entries / top_buckets > 0.7 * thr) t += 1e5;
     }
     return t;
 }
 inline void auto_plan(size_t n, bool g2, int glv_mode, int c_override, Plan &pl, int ba_mode = -1) {
+    // glv_mode: -1 automatic, 0 never, 1 two parts (φ), 2 four parts on G2 (ψ; G1 has no such endomorphism: two)
     double best = 1e300;
-    for (int glv = 0; glv <= 1; glv++) {
-        if (glv_mode == 0 && glv) continue;
-        if (glv_mode == 1 && !glv) continue;
-        if (glv && glv_mode < 0 && n > (1u << 22)) continue;  // automatic choice only where it was measured to pay
-        if (glv && 2 * n >= (1ull << 31)) continue;
+    for (int parts = 1; parts <= (g2 ? 4 : 2); parts *= 2) {
+        if (glv_mode == 0 && parts > 1) continue;
+        if (glv_mode == 1 && parts != 2) continue;
+        if (glv_mode == 2 && parts != (g2 ? 4 : 2)) continue;
+        if (parts > 1 && glv_mode < 0 && n > (1u << 22)) continue;  // automatic choice only where it was measured to pay
+        if (parts > 1 && (uint64_t)parts * n >= (1ull << 31)) continue;
         for (int c = 2; c <= 22; c++) {
             if (c_override > 0 && c != c_override) continue;
-            double t = plan_time_us(n, g2, glv, c, ba_mode);
-            if (t < best) { best = t; pl.c = c; pl.glv = glv; }
+            double t = plan_time_us(n, g2, parts, c, ba_mode);
+            if (t < best) { best = t; pl.c = c; pl.parts = parts; }
         }
     }
-    pl.nwin = plan_windows(pl.glv, pl.c, &pl.split);
+    pl.glv = pl.parts > 1;
+    pl.nwin = plan_windows(pl.parts, pl.c, &pl.split);
     pl.nbw = 1u << (pl.c - 1);
     pl.nb = pl.nbw * (uint32_t)pl.nwin;
 }

@@ -75,7 +75,8 @@ def executed_accumulate_fpmul(n, g2, plan, ba_rounds):
     madd, aff = (28, 17) if g2 else (10, 6)
     lvl2 = (9 if g2 else 3) / 32.0
     c, W, glv = plan["window_bits"], plan["windows"], plan["glv"]
-    entries = n * (2 if glv else 1) * (W - 1 if glv == 2 else W) * (1 - 2.0 ** -c)
+    parts = 1 if glv == 0 else (2 if glv <= 2 else 4)          # b200msm_last_plan: 1 / 2 two parts, 3 / 4 four parts (G2)
+    entries = n * parts * (W - 1 if glv in (2, 4) else W) * (1 - 2.0 ** -c)
     tot = 0.0
     for r in range(1, ba_rounds + 1):
         tot += entries / 2 ** r * (aff + lvl2)
@@ -819,7 +820,7 @@ def run_ours(args):
         _, _, fpmul_total, _ = work_model(n_total, g2)     # single-problem numerator
         acc_s = ph["accumulate"] * 1e-3
         imad_peak = cx.peak["imad_per_s"]
-        entries_per_bucket = n * (2 if plan["glv"] else 1) / 2.0 ** (plan["window_bits"] - 1)
+        entries_per_bucket = n * (1 if plan["glv"] == 0 else (2 if plan["glv"] <= 2 else 4)) / 2.0 ** (plan["window_bits"] - 1)
         ba_rounds = 3 if entries_per_bucket >= 24 else (1 if entries_per_bucket >= 12 else 0)   # csrc/plan.h ba_rounds_for
         exec_fpmul = executed_accumulate_fpmul(n, g2, plan, ba_rounds)
         achieved = fpmul_acc * FPMUL_IMAD / acc_s
@@ -839,7 +840,7 @@ def run_ours(args):
             "points_per_s": n_total / (dev_ms * 1e-3),
             "config": {"workload": f"{args.group.upper()} MSM 2^{args.logn} points per GPU x {world} GPU(s) = {n_total} points",
                        "window_bits": c, "windows": W,
-                       "engine_plan": {**plan, "note": "glv 2 = scalars split k1 + k2*lambda over (P, phi(P)), unsigned top digit; "
+                       "engine_plan": {**plan, "note": "glv 2 = scalars split k1 + k2*lambda over (P, phi(P)), unsigned top digit (4: four parts over the psi images, G2); "
                                                        "window_bits/windows above are the canonical c* of the work model (roofline numerator)"},
                        "scalars": "uniform mod r, Montgomery form (VariableBaseMSM::msm)",
                        "bases": "random subgroup points k_i*G, affine, resident in HBM",

@@ -136,8 +136,12 @@ int b200msm_set_window_bits(int c);
 /* GLV split of every scalar into two 128-bit halves k = k1 + k2·λ over (P, φ(P) = (β·x, y)) — half
  * the scalar bits, so half the windows to reduce and half the on-device Horner chain, at the same
  * number of bucket additions. -1 = automatic (time model; the default: on for n ≤ 2^22), 0 = never,
- * 1 = always. Results are the same group elements either way. */
+ * 1 = always (two parts). Results are the same group elements either way. */
 int b200msm_set_glv(int mode);
+/* (mode 2: on G2, FOUR parts instead of two — the base-|z| digits of the scalar over Q, −ψ(Q), ψ²(Q), −ψ³(Q) with ψ the
+ * untwist-Frobenius-twist endomorphism, which acts on the subgroup as multiplication by the curve parameter z: a quarter
+ * of the windows to reduce and of the dependent doublings of the Horner chain.  G1 has no such endomorphism: mode 2 means
+ * two parts there.  The automatic mode chooses among none / two / four by its time model.) */
 /* Batched-affine pairing rounds in front of the XYZZ bucket accumulation: the sorted entry array is halved
  * `rounds` times by affine additions that share one field inversion per ≈10^5 pairs (6 products per addition
  * instead of 10 for G1, 17 instead of 28 for G2); what is left of every bucket is accumulated in XYZZ form.
@@ -179,7 +183,8 @@ int b200msm_set_max_chunk(size_t max_points_per_pass);
  * [7] accumulate launches. Filled only when b200msm_set_profiling(1). */
 int b200msm_set_profiling(int on);
 /* Plan of the most recent pass on this thread's device: [0] window bits c, [1] windows,
- * [2] GLV (0 off, 1 on, 2 on with the unsigned top digit), [3] fixed-base table used. */
+ * [2] GLV (0 off; 1 / 2 two parts with a carry window / with the unsigned top digit; 3 / 4 the same with four parts, G2),
+ * [3] fixed-base table used. */
 int b200msm_last_plan(int out[4]);
 /* The plan `auto_plan` would pick for an n-point MSM under the given GLV mode (-1 / 0 / 1), without
  * touching a device: [0] window bits, [1] windows, [2] GLV (0 / 1 / 2), [3] buckets in all. */

@@ -13,16 +13,20 @@ static int failures = 0;
 int main() {
     for (int g2 = 0; g2 < 2; g2++) {
         for (int logn = 1; logn <= 27; logn++) {
-            for (int mode = -1; mode <= 1; mode++) {
+            for (int mode = -1; mode <= 2; mode++) {
                 Plan p;
                 auto_plan((size_t)1 << logn, g2, mode, 0, p);
                 CHECK(p.c >= 2 && p.c <= 22 && p.nwin >= 1);
                 CHECK(p.nbw == 1u << (p.c - 1) && p.nb == p.nbw * (uint32_t)p.nwin);
+                CHECK(p.parts == 1 || p.parts == 2 || (p.parts == 4 && g2));
+                CHECK(p.glv == (p.parts > 1));
+                const int bits = 256 / p.parts;       // width of a part of the decomposed scalar
                 if (!p.glv) CHECK(p.c * p.nwin >= 256 && (p.nwin - 1) * p.c < 256);
-                else if (p.split) CHECK(128 % p.c == 0 && p.nwin == 128 / p.c + 1);
-                else CHECK(p.c * p.nwin >= 129 && (p.nwin - 1) * p.c < 129);
+                else if (p.split) CHECK(bits % p.c == 0 && p.nwin == bits / p.c + 1);
+                else CHECK(p.c * p.nwin >= bits + 1 && (p.nwin - 1) * p.c < bits + 1);
                 if (mode == 0) CHECK(!p.glv);
-                if (mode == 1) CHECK(p.glv);
+                if (mode == 1) CHECK(p.parts == 2);
+                if (mode == 2) CHECK(p.parts == (g2 ? 4 : 2));
                 if (mode == -1 && logn > 22) CHECK(!p.glv);
             }
             for (int c = 2; c <= 22; c++) {  // an explicit width is honoured
@@ -39,7 +43,8 @@ int main() {
         auto_plan(1u << 20, g2, 0, 0, p, 0); CHECK(p.c == 16 && p.nwin == 16);
         auto_plan(1u << 24, g2, 0, 0, p, 0); CHECK(p.c == 20 && p.nwin == 13);
         CHECK(ba_rounds_for(64) == 3 && ba_rounds_for(16) == 1 && ba_rounds_for(4) == 0);
-        auto_plan(1u << 20, g2, -1, 0, p); CHECK(p.glv && p.split && p.c == 16 && p.nwin == 9);
+        auto_plan(1u << 20, g2, -1, 0, p); CHECK(p.glv && p.split && p.c == 16 && (p.parts == 2 ? p.nwin == 9 : (g2 && p.parts == 4 && p.nwin == 5)));
+        auto_plan(1u << 20, g2, 2, 0, p); CHECK(p.glv && p.split && p.c == 16 && p.nwin == (g2 ? 5 : 9) && p.parts == (g2 ? 4 : 2));
     }
     std::printf(failures ? "FAILED (%d)\n" : "ok\n", failures);
     return failures ? 1 : 0;

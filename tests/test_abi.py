@@ -121,8 +121,10 @@ def test_planner_host_logic(eng):
         for logn in (16, 20, 22, 24):                   # with the batched-affine rounds the model may go one width down
             c, W, glv, nb = _plan(eng, g, 1 << logn, 0)
             assert glv == 0 and c * W >= 256 and W == -(-256 // c) and abs(c - work_model(1 << logn, g)[0]) <= 2
-        for logn in (16, 18, 20):
-            assert _plan(eng, g, 1 << logn, -1)[:3] == (16, 9, 2)
+        for logn in (16, 18, 20):   # two 128-bit parts over (P, phi(P)) on G1; four 64-bit parts over the psi images on G2
+            assert _plan(eng, g, 1 << logn, -1)[:3] in (((16, 5, 4), (16, 9, 2)) if g else ((16, 9, 2),))
+            assert _plan(eng, g, 1 << logn, 1)[:3] == (16, 9, 2)
+            assert _plan(eng, g, 1 << logn, 2)[:3] == ((16, 5, 4) if g else (16, 9, 2))
         for logn in (23, 24, 26):
             assert _plan(eng, g, 1 << logn, -1)[2] == 0
         # forced GLV: a width dividing 128 has 128/c + 1 windows, any other keeps the carry window (c·W ≥ 129)
