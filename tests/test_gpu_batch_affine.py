@@ -161,3 +161,59 @@ def test_graph_replay_is_bit_exact(eng, cref, knobs, g2):
         eng.run_device(G, bases.data_ptr(), scalars.data_ptr(), n, True, out.data_ptr(), 0)
         torch.cuda.synchronize()
         assert cref.affine_equal(g2, out.cpu().numpy().view(np.uint64), exp)
+
+
+def test_two_pipeline_rounds_repeated(eng, cref):
+    """Large rounds run as two half-range pipelines on two streams, which may drift a round apart: every array a
+    pipeline owns must keep its place across rounds (a first version moved part 1's scratch with the round's plan and
+    lost ≈1 result in 25).  Back-to-back table + plain MSMs at 2^20, repeated, results checked every time."""
+    import torch
+
+    g2, n = 0, 1 << 20
+    st = torch.cuda.current_stream().cuda_stream
+    c, W = eng.table_plan(g2, n)
+    table = torch.empty((W, n, 12), dtype=torch.int64, device="cuda")
+    scalars = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    eng.synth_bases_device(g2, 6100, n, table.data_ptr())
+    eng.table_build_device(g2, table.data_ptr(), n, c, table.data_ptr(), st)
+    out = torch.zeros((2, 18), dtype=torch.int64, device="cuda")
+    for it in range(10):
+        eng.synth_scalars_device(6200 + it, n, True, scalars.data_ptr())
+        eng.run_table_device(g2, table.data_ptr(), n, c, scalars.data_ptr(), n, True, out[0].data_ptr(), st)
+        eng.run_device(g2, table.data_ptr(), scalars.data_ptr(), n, True, out[1].data_ptr(), st)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().view(np.uint64)
+        exp = cref.msm_by_dlog(g2, 6100, cref.synth_scalars(6200 + it, n, False))
+        assert cref.affine_equal(g2, got[0], exp), ("table", it)
+        assert cref.affine_equal(g2, got[1], exp), ("plain", it)
+
+
+@pytest.mark.parametrize("n", [1, 5, 700, 20011, (1 << 16) + 3])
+def test_g2_four_part_decomposition(eng, cref, knobs, n):
+    """b200msm_set_glv(2): G2 scalars as four base-|z| digits over Q, −ψ(Q), ψ²(Q), −ψ³(Q) (csrc/gls4.cuh) — against
+    the two-part split, no split, and the C oracle; with and without batched-affine rounds; identity bases included"""
+    g2 = 1
+    bases = cref.synth_bases(g2, 7100 + n, n)
+    if n > 4:
+        bases[3] = 0                                            # an identity base: all its images are the identity too
+    sm = cref.synth_scalars(7200 + n, n, True)
+    sc = cref.synth_scalars(7200 + n, n, False)
+    if n > 4:
+        sc[0] = 0
+        sc[1] = np.array(o.int_to_limbs(o.R_ORDER - 1, 4), dtype=np.uint64)
+        sc[2] = np.array(o.int_to_limbs((-o.BLS_X) ** 3, 4), dtype=np.uint64)     # digits (0, 0, 0, 1)
+        sm = np.array([o.scalar_to_limbs(o.limbs_to_int(r), True) for r in sc.tolist()], dtype=np.uint64)
+    exp = cref.msm(g2, bases, sc, 0)
+    for mode in (2, 1, 0):
+        assert knobs.b200msm_set_glv(mode) == 0
+        for rounds, c in ((-1, 0), (0, 0), (2, 8), (3, 13)):
+            assert knobs.b200msm_set_batch_affine(rounds) == 0 and knobs.b200msm_set_window_bits(c) == 0
+            assert cref.affine_equal(g2, eng.G2Projective.msm(bases, sm), exp), (mode, rounds, c)
+            assert cref.affine_equal(g2, eng.G2Projective.msm_bigint(bases, sc), exp), (mode, rounds, c)
+    assert knobs.b200msm_set_glv(2) == 0 and knobs.b200msm_set_window_bits(0) == 0 and knobs.b200msm_set_batch_affine(-1) == 0
+    eng.G2Projective.msm(bases, sm)
+    assert eng.last_plan()["glv"] in (3, 4)
+    # G1 has no ψ: mode 2 means the two-part split there
+    b1 = cref.synth_bases(0, 7300 + n, n)
+    assert cref.affine_equal(0, eng.G1Projective.msm(b1, sm), cref.msm(0, b1, sc, 0))
+    assert eng.last_plan()["glv"] in (1, 2)
