@@ -53,11 +53,12 @@ inline double plan_time_us(size_t n, bool g2, int parts, int c, int ba_mode = -1
     const double madd = g2 ? 28 : 10, add = g2 ? 40 : 14, pipe = 18.5e6;  // IMAD per µs
     // one thread per bucket: below ≈2.5 warps per scheduler (4 × 148 of them) the dependent-issue latency of the
     // product chain shows (measured with 2^15 buckets: 0.6 of the pipe)
-    // (GLV: the φ(P) entries read x from the β·x table and y from the base record — measured 2.5 % / 6 % slower)
+    // (GLV, round 1: the φ(P) entries read x from the β·x table and y from the base record — 2.5 % / 6 % slower in the XYZZ-only kernel;
+    //  with the batched-affine rounds in front the difference is gone)
     const double wps = W * std::pow(2.0, c - 1) / 32 / 592;
     // (four parts on G2: the images come from three full-point tables, 768 B of gather per base instead of 288 — measured
     // with the batched-affine rounds: accumulate 15.15 → 15.5 ms at 2^20, 57.6 → 59.6 at 2^22; two parts cost nothing there)
-    const double eff = std::min(g2 ? 0.76 : 0.88, 0.35 * wps) * (glv ? (g2 ? (parts == 4 ? 0.97 : 1.0) : 0.975) : 1.0);
+    const double eff = std::min(g2 ? 0.76 : 0.88, 0.35 * wps) * (glv && parts == 4 ? 0.97 : 1.0);   // (G1 2^22: accumulate 18.47 ms with and without the two-part split)
     double t = entries * Wacc * madd * 588 / (pipe * eff) * ba_time_factor(entries / std::pow(2.0, c - 1), g2, ba_mode);
     t += W * std::pow(2.0, c - 1) * 2 * add * 588 / (pipe * 0.55);
     t += (split ? (W - 2) * c + c - 1 : (W - 1) * c) * (g2 ? 11.0 : 3.4) + 250;
