@@ -365,6 +365,31 @@ struct PassOpts {
     const Plan *plan = nullptr;
     bool into = false, finish = true;
 };
+// Shapes of the batched-affine rounds of a pass: per round the launch plan of one pipeline (the whole slot range, or
+// one of its halves when the rounds run as two pipelines), and the scratch one pipeline needs over ALL rounds — the
+// maxima, because the two pipelines may be a round apart and the per-round sizes are not monotone (K shrinks with the
+// slot count, so NT = ⌈slots/K⌉ can grow from one round to the next).
+struct BaLayout {
+    bool split = false;
+    BaPlan bp[3];
+    size_t pre_el = 0, t_el = 0, u_el = 0;   // elements per pipeline: prefix, T / prefix2, U
+};
+BaLayout ba_layout(size_t s1, int R, int sm_count) {
+    static const bool split_ok = !(getenv("B200MSM_BA_SPLIT") && atoi(getenv("B200MSM_BA_SPLIT")) == 0);
+    BaLayout L;
+    L.split = split_ok && s1 >= ((size_t)1 << 20);
+    size_t s_out = s1;
+    for (int r = 0; r < R; r++) {
+        const size_t s_part = L.split ? s_out / 2 + ((size_t)1 << (5 + R)) + 1 : s_out;
+        L.bp[r] = ba_plan(s_part, sm_count);
+        L.pre_el = std::max(L.pre_el, (size_t)L.bp[r].NT * L.bp[r].K);
+        L.t_el = std::max<size_t>(L.t_el, L.bp[r].NT);
+        L.u_el = std::max<size_t>(L.u_el, L.bp[r].NU);
+        s_out = (s_out + 1) / 2;
+    }
+    return L;
+}
+
 // Plan + scratch reservation of one pass (may allocate: never inside a graph capture).
 int pass_prepare(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v, const void *d_scalars_v, size_t n, int mont,
                  void *d_out_v, const TableRef *tbl, const PassOpts &po, PassArgs &pa) {
@@ -434,15 +459,12 @@ int pass_prepare(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v,
         if (int rc = cx.endo.reserve(n * (size_t)W * 4 * (pl.parts == 4 ? 6 : 1))) return rc;
     if (R > 0) {
         const size_t FB = (size_t)W * 4, s1 = (slots_max + 1) / 2;
-        // round 1 is the largest; it may run unsplit or as two half-range pipelines (pass_issue_main), whose plans
-        // round up separately and may use a smaller K (more threads): reserve for whichever is larger
-        const BaPlan bp = ba_plan(s1, cx.sm_count), bh = ba_plan(s1 / 2 + ((size_t)1 << (5 + R)) + 1, cx.sm_count);
-        const size_t pre_el = std::max((size_t)bp.NT * bp.K, 2 * (size_t)bh.NT * bh.K) + 65536;
-        const size_t t_el = std::max<size_t>(bp.NT, 2 * (size_t)bh.NT) + 4096, u_el = std::max<size_t>(bp.NU, 2 * (size_t)bh.NU) + 1024;
-        if (int rc = cx.ba_prefix.reserve(pre_el * FB)) return rc;
-        if (int rc = cx.ba_T.reserve(t_el * FB)) return rc;
-        if (int rc = cx.ba_prefix2.reserve(t_el * FB)) return rc;
-        if (int rc = cx.ba_U.reserve(u_el * FB)) return rc;
+        const BaLayout bl = ba_layout(s1, R, cx.sm_count);
+        const size_t np = bl.split ? 2 : 1;
+        if (int rc = cx.ba_prefix.reserve((np * bl.pre_el + 256) * FB)) return rc;
+        if (int rc = cx.ba_T.reserve((np * bl.t_el + 256) * FB)) return rc;
+        if (int rc = cx.ba_prefix2.reserve((np * bl.t_el + 256) * FB)) return rc;
+        if (int rc = cx.ba_U.reserve((np * bl.u_el + 256) * FB)) return rc;
         // one output array per round (NOT a ping-pong pair: with the rounds running as two half-range pipelines on two
         // streams, the pipeline that is a round ahead would overwrite what the other has not read yet)
         size_t sr = s1;
@@ -511,29 +533,26 @@ int pass_issue_main(DeviceCtx &cx, const PassArgs &pa, cudaStream_t st, bool pro
         // Large rounds run as TWO interleaved pipelines over the two halves of the slot range, on two streams: the
         // second level + inversion of a round are three small latency-bound launches (≈0.1–0.2 ms in all) during
         // which a single pipeline leaves the GPU almost idle; with two, the other half's large kernels fill it.
-        static const bool split_ok = !(getenv("B200MSM_BA_SPLIT") && atoi(getenv("B200MSM_BA_SPLIT")) == 0);
-        const bool split = split_ok && s_out >= ((size_t)1 << 20);
+        // Each pipeline owns a fixed part of every scratch array for all rounds (ba_layout).
+        const BaLayout bl = ba_layout(s_out, pa.R, cx.sm_count);
+        const bool split = bl.split;
         const int align_log = split ? 6 + pa.R : 0;
         const size_t FW = (size_t)W;   // u32 words per field element
         if (split) {
             CUDA_TRY(cudaEventRecord(cx.ev_fork, st));
             CUDA_TRY(cudaStreamWaitEvent(cx.aux_stream, cx.ev_fork, 0));
         }
-        size_t o1 = 0, o2 = 0, o3 = 0;   // part 1's scratch: fixed offsets (the first round's sizes) for ALL rounds — the pipelines may be a
-                                         // round apart, and offsets that shrank with the round would put part 1's round r+1 on top of part 0's round r
         for (int r = 0; r < pa.R; r++) {
             uint32_t *out = cx.ba_pts[r].as<uint32_t>();
-            const size_t s_part = split ? s_out / 2 + ((size_t)1 << (5 + pa.R)) + 1 : s_out;
-            const BaPlan bp = ba_plan(s_part, cx.sm_count);
-            if (r == 0) { o1 = (size_t)bp.NT * bp.K; o2 = bp.NT; o3 = bp.NU; }
             for (int part = 0; part < (split ? 2 : 1); part++) {
-                (g2 ? launch_ba_round_g2 : launch_ba_round_g1)(r == 0, src, vals, endo_x, n_pts, start + pa.nb, r, bp,
-                                                               cx.ba_prefix.as<uint32_t>() + (part ? o1 : 0) * FW, cx.ba_T.as<uint32_t>() + (part ? o2 : 0) * FW,
-                                                               cx.ba_prefix2.as<uint32_t>() + (part ? o2 : 0) * FW, cx.ba_U.as<uint32_t>() + (part ? o3 : 0) * FW, out,
+                (g2 ? launch_ba_round_g2 : launch_ba_round_g1)(r == 0, src, vals, endo_x, n_pts, start + pa.nb, r, bl.bp[r],
+                                                               cx.ba_prefix.as<uint32_t>() + (part ? bl.pre_el : 0) * FW,
+                                                               cx.ba_T.as<uint32_t>() + (part ? bl.t_el : 0) * FW,
+                                                               cx.ba_prefix2.as<uint32_t>() + (part ? bl.t_el : 0) * FW,
+                                                               cx.ba_U.as<uint32_t>() + (part ? bl.u_el : 0) * FW, out,
                                                                part ? cx.aux_stream : st, part, align_log, img_full);
             }
             src = out;
-            s_out = (s_out + 1) / 2;
         }
         if (split) {
             CUDA_TRY(cudaEventRecord(cx.ev_join, cx.aux_stream));

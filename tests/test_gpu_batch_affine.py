@@ -217,3 +217,24 @@ def test_g2_four_part_decomposition(eng, cref, knobs, n):
     b1 = cref.synth_bases(0, 7300 + n, n)
     assert cref.affine_equal(0, eng.G1Projective.msm(b1, sm), cref.msm(0, b1, sc, 0))
     assert eng.last_plan()["glv"] in (1, 2)
+
+
+@pytest.mark.parametrize("g2,n", [(0, 1 << 19), (0, 3 << 18), (0, (1 << 19) + 12345), (1, 1 << 19), (1, 3 << 17)])
+def test_two_pipeline_rounds_sizes_between_the_clamps(eng, cref, g2, n):
+    """sizes whose per-pipeline plans are NOT at the K = 32 clamp: there the thread count of a later round can exceed
+    the first round's (K halves with the slot count), so a pipeline's scratch must be sized by the maximum over the
+    rounds — the 8-GPU Groth16 shape (2^19 points per GPU) found a layout that used the first round's sizes"""
+    import torch
+
+    aw, jw = (24, 36) if g2 else (12, 18)
+    bases = torch.empty((n, aw), dtype=torch.int64, device="cuda")
+    scalars = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    out = torch.zeros(jw, dtype=torch.int64, device="cuda")
+    eng.synth_bases_device(g2, 8100 + g2, n, bases.data_ptr())
+    st = torch.cuda.current_stream().cuda_stream
+    for it in range(4):
+        eng.synth_scalars_device(8200 + it, n, True, scalars.data_ptr())
+        eng.run_device(g2, bases.data_ptr(), scalars.data_ptr(), n, True, out.data_ptr(), st)
+        torch.cuda.synchronize()
+        exp = cref.msm_by_dlog(g2, 8100 + g2, cref.synth_scalars(8200 + it, n, False))
+        assert cref.affine_equal(g2, out.cpu().numpy().view(np.uint64), exp), it
