@@ -213,7 +213,8 @@ __device__ __forceinline__ void block_tree_sum(xyzz<F> &acc, uint32_t *smem) {
         if ((int)threadIdx.x < stride) {
             xyzz<F> o;
             xyzz_load(o, smem + (size_t)threadIdx.x * PW);
-            xyzz_add(acc, o);                         // inlined: both operands stay in registers
+            if (field_words<F>::value == 12) xyzz_add(acc, o);   // G1: inlined, both operands stay in registers (witness-like 2^20: 5.34 → 4.81 ms)
+            else xyzz_add_ni(acc, o);                            // G2: out of line (the inlined Fp2 tree took ptxas five minutes for ≈1 % of a rare path)
         }
         __syncthreads();
     }

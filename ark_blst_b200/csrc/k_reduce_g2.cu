@@ -18,13 +18,4 @@ void launch_tree_level_g2(const uint32_t *Sin, size_t sin_stride, const uint32_t
     k_tree_level<fp2><<<blocks_for(quads * 4, 128), 128, 0, st>>>(Sin, sin_stride, Vin, Cin, cin_stride, Sout, Vout, Cout,
                                                                  out_stride, S, j, nwin);
 }
-void launch_combine_g2(const uint32_t *Sroot, const uint32_t *V, const uint32_t *Croot, size_t stride, int logS, int log2M,
-                       int nwin, int c, int split_top, uint32_t *wsum, uint32_t *out, cudaStream_t st) {
-    count_launch();
-    k_combine<fp2><<<1, 128, 0, st>>>(Sroot, V, Croot, stride, logS, log2M, nwin, c, split_top, wsum, out);
-}
-void launch_sum_partials_g2(const uint32_t *partials, int count, uint32_t *out, cudaStream_t st) {
-    count_launch();
-    k_sum_partials<fp2><<<1, 32, 0, st>>>(partials, count, out);
-}
 }  // namespace b200msm

@@ -130,6 +130,11 @@ k_tree_level(const uint32_t *__restrict__ Sin, size_t sin_stride, const uint32_t
     if (live) q_store(pd, a);
 }
 
+// out-of-line copies of the quad operations for k_combine: the kernel is a chain of dependent point operations of ≈7 µs
+// (G1) / ≈20 µs (G2) each, so a call costs nothing, while the fully inlined Fp2 version took ptxas five minutes
+template <class F> __device__ __noinline__ void q_dbl_ni(F &A) { q_dbl(A); }
+template <class F> __device__ __noinline__ void q_add_ni(F &A, const F &B) { q_add(A, B); }
+
 // Per window: value_w = C_root + 2^log2M·(Σ_k 2^k V_k) + S_root (one quad per window, Horner over
 // k), then result = Σ_w 2^(c·w)·value_w by Horner from the top window (warp 0), written as a
 // Jacobian point (blst_p1 / blst_p2 layout). One block of 128 threads = 32 quads.
@@ -150,7 +155,7 @@ k_combine(const uint32_t *__restrict__ Sroot, const uint32_t *__restrict__ V, co
     split_top &= 1;
     if (top_aside && threadIdx.x >= 96) {          // warp-uniform: the whole warp runs the chain, quad 24 stores
         q_load(a, Sroot + (size_t)(nwin - 1) * stride * PW);
-        for (int k = 0; k < c - 1; k++) q_dbl(a);
+        for (int k = 0; k < c - 1; k++) q_dbl_ni(a);
         if (qd == 24) q_store(wsum + (size_t)nwin * PW, a);
     } else
     for (int base = 0; base < nwin; base += 32) {  // block-uniform trip count
@@ -158,24 +163,24 @@ k_combine(const uint32_t *__restrict__ Sroot, const uint32_t *__restrict__ V, co
         q_set_inf(acc);
         const uint32_t *v = V + (size_t)w * stride * PW;
         for (int k = logS - 1; k >= 0; k--) {      // T = Σ_k 2^k V_k
-            q_dbl(acc);
+            q_dbl_ni(acc);
             q_load(a, v + (size_t)k * PW);
-            q_add(acc, a);
+            q_add_ni(acc, a);
         }
-        for (int k = 0; k < log2M; k++) q_dbl(acc);
+        for (int k = 0; k < log2M; k++) q_dbl_ni(acc);
         if (Croot) {
             q_load(a, Croot + (size_t)w * stride * PW);
-            q_add(acc, a);
+            q_add_ni(acc, a);
         }
         q_load(a, Sroot + (size_t)w * stride * PW);
-        q_add(acc, a);
+        q_add_ni(acc, a);
         if (split_top && !top_aside) {             // upper half of the unsigned top digit: + 2^(c−1)·Σ buckets
             const bool extra = w == nwin - 1;      // (every quad runs the chain: q_dbl needs whole warps)
-            for (int k = 0; k < c - 1; k++) q_dbl(a);
+            for (int k = 0; k < c - 1; k++) q_dbl_ni(a);
             F zero;
             q_set_inf(zero);
             a = q_sel(extra, a, zero);
-            q_add(acc, a);
+            q_add_ni(acc, a);
         }
         if (base + qd < nwin) q_store(wsum + (size_t)(base + qd) * PW, acc);
     }
@@ -187,15 +192,15 @@ k_combine(const uint32_t *__restrict__ Sroot, const uint32_t *__restrict__ V, co
         q_load(acc, wsum + (size_t)top * PW);
         if (top_aside) {
             q_load(a, wsum + (size_t)nwin * PW);
-            q_add(acc, a);
+            q_add_ni(acc, a);
         }
         top--;
     }
     for (int ww = top; ww >= 0; ww--) {
         if (ww != top)                             // nothing to double before the top window
-            for (int k = 0; k < c; k++) q_dbl(acc);
+            for (int k = 0; k < c; k++) q_dbl_ni(acc);
         q_load(a, wsum + (size_t)ww * PW);
-        q_add(acc, a);
+        q_add_ni(acc, a);
     }
     F r = q_to_jac(acc);
     if (threadIdx.x < 3) f_store(out + threadIdx.x * W, r);
