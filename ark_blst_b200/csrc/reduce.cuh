@@ -6,6 +6,13 @@
 
 namespace b200msm {
 
+// out-of-line copies of the quad operations: k_combine is a chain of dependent point operations of ≈7 µs (G1) / ≈20 µs
+// (G2) each, so a call costs nothing, while the fully inlined Fp2 version took ptxas five minutes — and ran SLOWER
+// (G2 combine 1.31 → 1.18 ms out of line: the inlined body does not fit the instruction cache; G1 0.60 → 0.61).
+// (The same for the G2 reduction levels was measured and is slower — reduce 1.48 → 1.60 ms — they stay inlined.)
+template <class F> __device__ __noinline__ void q_dbl_ni(F &A) { q_dbl(A); }
+template <class F> __device__ __noinline__ void q_add_ni(F &A, const F &B) { q_add(A, B); }
+
 // ---- bucket reduction, lower part: running sums ----------------------------------------------
 // Weighted sum with 0-based weights, Wsum0(X) = Σ i·X[i], by segments of m:
 //     Wsum0(X) = Σ_s A[s] + m·Wsum0(R),   A[s] = Wsum0(segment s),  R[s] = Sum(segment s)
@@ -129,11 +136,6 @@ k_tree_level(const uint32_t *__restrict__ Sin, size_t sin_stride, const uint32_t
     q_add(a, b);
     if (live) q_store(pd, a);
 }
-
-// out-of-line copies of the quad operations for k_combine: the kernel is a chain of dependent point operations of ≈7 µs
-// (G1) / ≈20 µs (G2) each, so a call costs nothing, while the fully inlined Fp2 version took ptxas five minutes
-template <class F> __device__ __noinline__ void q_dbl_ni(F &A) { q_dbl(A); }
-template <class F> __device__ __noinline__ void q_add_ni(F &A, const F &B) { q_add(A, B); }
 
 // Per window: value_w = C_root + 2^log2M·(Σ_k 2^k V_k) + S_root (one quad per window, Horner over
 // k), then result = Σ_w 2^(c·w)·value_w by Horner from the top window (warp 0), written as a
