@@ -38,7 +38,7 @@ def test_synth_matches_oracle(eng, cref):
         assert np.array_equal(sc.cpu().numpy().view(np.uint64), cref.synth_scalars(456, n, False))
 
 
-@pytest.mark.parametrize("g2,logn", [(0, 16), (0, 20), (0, 22), (0, 24), (1, 18), (1, 20), (1, 22)])
+@pytest.mark.parametrize("g2,logn", [(0, 16), (0, 20), (0, 22), (0, 23), (0, 24), (1, 18), (1, 20), (1, 21), (1, 22)])
 def test_dlog_closed_form(eng, cref, g2, logn):
     """Σ sᵢ·(kᵢ·G) = (Σ sᵢkᵢ mod r)·G at BASELINE sizes"""
     import torch
@@ -53,7 +53,7 @@ def test_dlog_closed_form(eng, cref, g2, logn):
         _, canon = _dev_inputs(eng, torch, g2, sb, ss, n, False)
         L = eng._lib.lib
         try:
-            assert L.b200msm_set_glv(1 if logn > 22 else 0) == 0
+            assert L.b200msm_set_glv((1 if logn > 22 else 0) if not g2 else 2) == 0   # (G2: four parts at full size too)
             assert cref.affine_equal(g2, _run(eng, torch, g2, bases, canon, n, False), exp)
         finally:
             L.b200msm_set_glv(-1)
