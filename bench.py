@@ -336,11 +336,15 @@ class Case:
         torch.cuda.synchronize()
 
     def combine(self):
+        """the multi-GPU exchange of the path (ark_blst_b200/dist.py): one Jacobian partial per rank all-gathered over
+        NCCL, final addition on rank 0 by k_sum_partials"""
+        from ark_blst_b200 import dist as msm_dist
+
         cx = self.cx
         if cx.world > 1:
-            cx.dist.all_gather_into_tensor(self.gathered.view(-1), self.partial)
+            msm_dist.gather_partials(self.partial, cx.world, cx.dist, out=self.gathered)
             if cx.rank == 0:
-                cx.eng.sum_partials_device(self.G, self.gathered.data_ptr(), cx.world, self.result.data_ptr(), cx.stream)
+                msm_dist.combine_on_device(self.G, self.gathered, cx.stream, out=self.result)
         else:
             self.result.copy_(self.partial)
 
@@ -422,6 +426,8 @@ class Case:
     def time_e2e(self, steps, warmup, call):
         """`call()` → this rank's partial as host limbs (through the host-buffer C-ABI); partials → device,
         NCCL all-gather, final addition on rank 0, result read back. Wall clock bracketed by barriers, max over ranks."""
+        from ark_blst_b200 import dist as msm_dist
+
         cx, torch, np = self.cx, self.cx.torch, self.np
         hpart = torch.zeros(self.jw, dtype=torch.int64, pin_memory=True)
 
@@ -430,9 +436,9 @@ class Case:
             if cx.world > 1:
                 hpart.numpy().view(np.uint64)[:] = out
                 self.partial.copy_(hpart, non_blocking=True)
-                cx.dist.all_gather_into_tensor(self.gathered.view(-1), self.partial)
+                msm_dist.gather_partials(self.partial, cx.world, cx.dist, out=self.gathered)
                 if cx.rank == 0:
-                    cx.eng.sum_partials_device(self.G, self.gathered.data_ptr(), cx.world, self.result.data_ptr(), cx.stream)
+                    msm_dist.combine_on_device(self.G, self.gathered, cx.stream, out=self.result)
                     return self.result.cpu().numpy().view(np.uint64)
                 torch.cuda.synchronize()
             return out
@@ -453,8 +459,10 @@ def side_steps(args):
 
 def block_msm(cx, args, g2, n_total, tag, name):
     """A BASELINE config as a strong-scaling block: an n_total-point MSM sharded evenly over the ranks."""
+    from ark_blst_b200.dist import shard_range
+
     steps, warmup = side_steps(args)
-    lo, hi = n_total * cx.rank // cx.world, n_total * (cx.rank + 1) // cx.world
+    lo, hi = shard_range(n_total, cx.rank, cx.world)
     case = Case(cx, g2, hi - lo, tag)
     cx.L.b200msm_set_profiling(1)
     ms, ph, _ = case.time_device(steps, warmup)
@@ -505,8 +513,10 @@ def block_groth16(cx, args, logn, scalars_kind, lanes=4, table=False, steps=None
 
     if steps is None:
         steps, warmup = side_steps(args)
+    from ark_blst_b200.dist import shard_range
+
     n_total = 1 << logn
-    lo, hi = n_total * cx.rank // cx.world, n_total * (cx.rank + 1) // cx.world
+    lo, hi = shard_range(n_total, cx.rank, cx.world)
     n = hi - lo
     cases, nonzero = [], 0.0
     for k, g2 in enumerate((1, 0, 0, 0)):  # G2 first: the tail left exposed at the end is a G1 one
