@@ -626,7 +626,7 @@ int pass_issue_main(DeviceCtx &cx, const PassArgs &pa, cudaStream_t st, bool pro
     mark();
     // 6. window values and Horner over the windows → one Jacobian point
     (g2 ? launch_combine_g2 : launch_combine_g1)(Sin, cx.treeV[cur].as<uint32_t>(), Cin ? Ccur : nullptr, tstride, logS, log2M,
-                                                 rwin, pa.c, ((pa.glv == 2 || pa.glv == 4) ? 1 : 0) | (getenv("B200MSM_TOP_ASIDE") && atoi(getenv("B200MSM_TOP_ASIDE")) == 0 ? 2 : 0), cx.wsum.as<uint32_t>(), pa.d_out, st);
+                                                 rwin, pa.c, (pa.glv == 2 || pa.glv == 4) ? 1 : 0, cx.wsum.as<uint32_t>(), pa.d_out, st);
     mark();
     if (st != caller_st) {
         CUDA_TRY(cudaEventRecord(cx.ev_tail_join, st));

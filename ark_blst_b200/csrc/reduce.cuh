@@ -153,8 +153,7 @@ k_combine(const uint32_t *__restrict__ Sroot, const uint32_t *__restrict__ V, co
     // doublings run on WARP 3 (idle whenever nwin ≤ 24 — and split_top means c | 128, c ≥ 8, nwin ≤ 17) next to the
     // window values instead of after them on everybody's critical path (−50 µs at c = 16); the result goes to
     // wsum[nwin] and is added when the Horner chain starts.
-    const bool top_aside = (split_top & 1) && !(split_top & 2) && nwin <= 24;   // (bit 1 of split_top: debugging switch, keeps the chain in line)
-    split_top &= 1;
+    const bool top_aside = split_top && nwin <= 24;
     if (top_aside && threadIdx.x >= 96) {          // warp-uniform: the whole warp runs the chain, quad 24 stores
         q_load(a, Sroot + (size_t)(nwin - 1) * stride * PW);
         for (int k = 0; k < c - 1; k++) q_dbl_ni(a);
