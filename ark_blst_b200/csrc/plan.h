@@ -62,9 +62,12 @@ inline double plan_time_us(size_t n, bool g2, int parts, int c, int ba_mode = -1
     double t = entries * Wacc * madd * 588 / (pipe * eff) * ba_time_factor(entries / std::pow(2.0, c - 1), g2, ba_mode);
     t += W * std::pow(2.0, c - 1) * 2 * add * 588 / (pipe * 0.55);
     t += (split ? (W - 2) * c + c - 1 : (W - 1) * c) * (g2 ? 11.0 : 3.4) + 250;
-    t += entries * W * 2.3e-5;
+    t += entries * Wacc * 2.3e-5;   // grouping (an entry of a split plan lands in ONE of the two top windows)
+    // a plain plan whose top window keeps only a few bits (c = 18 at 2^23: 3 bits) piles its n entries onto a handful
+    // of bucket counters: the grouping's atomics serialise (measured: digits 4.8 ms instead of 2.4 at 2^23)
+    if (!glv && 255 - ((int)W - 1) * c < c - 5) t += (double)n * 3e-4;
     if (glv) {
-        t += (double)n * (parts == 4 ? 12 : (g2 ? 2 : 1)) * 588 / (pipe * 0.5) + (double)n * (parts == 4 ? 1.2e-4 : 4e-5);  // image table(s), decomposition
+        t += (double)n * (parts == 4 ? 12 : (g2 ? 2 : 1)) * 588 / (pipe * 0.8) + (double)n * (parts == 4 ? 1.2e-4 : 2e-5);  // image table(s), decomposition (k_endo_table: 44 µs at G1 2^20)
         // a top window with few bits piles its entries into few buckets: block-cooperative path, ≈3.5× the cost
         // The halves are below λ ≈ 0.673·2^128, so the top window only uses ⌊λ / 2^(c(W−1))⌋ + 1 of its buckets.
         // When that is few, its entries pile up past the heavy-bucket threshold and go down the block-cooperative
@@ -84,7 +87,7 @@ inline void auto_plan(size_t n, bool g2, int glv_mode, int c_override, Plan &pl,
         if (glv_mode == 0 && parts > 1) continue;
         if (glv_mode == 1 && parts != 2) continue;
         if (glv_mode == 2 && parts != (g2 ? 4 : 2)) continue;
-        if (parts > 1 && glv_mode < 0 && n > (1u << 22)) continue;  // automatic choice only where it was measured to pay
+        if (parts > 1 && glv_mode < 0 && n > (1u << 23)) continue;  // automatic choice only where it was measured to pay (2^24: 77.4 ms plain, 80.0 split)
         if (parts > 1 && (uint64_t)parts * n >= (1ull << 31)) continue;
         for (int c = 2; c <= 22; c++) {
             if (c_override > 0 && c != c_override) continue;

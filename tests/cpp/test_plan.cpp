@@ -27,7 +27,7 @@ int main() {
                 if (mode == 0) CHECK(!p.glv);
                 if (mode == 1) CHECK(p.parts == 2);
                 if (mode == 2) CHECK(p.parts == (g2 ? 4 : 2));
-                if (mode == -1 && logn > 22) CHECK(!p.glv);
+                if (mode == -1 && logn > 23) CHECK(!p.glv);
             }
             for (int c = 2; c <= 22; c++) {  // an explicit width is honoured
                 Plan p;

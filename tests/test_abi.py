@@ -104,7 +104,7 @@ def test_planner_host_logic(eng):
     """auto_plan needs no device. Without GLV and without batched-affine rounds it lands on the work model's canonical c* of SURVEY
     §8(d) at 2^16 / 2^20 / 2^24 (13 / 16 / 20; 16 instead of 18 at 2^22, whose top window would be
     degenerate) with c·W ≥ 256; GLV takes c = 16 with the unsigned top digit (8 + 1 windows) where
-    it was measured to pay and is never picked automatically above 2^22 points."""
+    it was measured to pay and is never picked automatically above 2^23 points."""
     from bench import work_model
 
     L = eng._lib.lib
@@ -125,7 +125,7 @@ def test_planner_host_logic(eng):
             assert _plan(eng, g, 1 << logn, -1)[:3] in (((16, 5, 4), (16, 9, 2)) if g else ((16, 9, 2),))
             assert _plan(eng, g, 1 << logn, 1)[:3] == (16, 9, 2)
             assert _plan(eng, g, 1 << logn, 2)[:3] == ((16, 5, 4) if g else (16, 9, 2))
-        for logn in (23, 24, 26):
+        for logn in (24, 26):
             assert _plan(eng, g, 1 << logn, -1)[2] == 0
         # forced GLV: a width dividing 128 has 128/c + 1 windows, any other keeps the carry window (c·W ≥ 129)
         c, W, glv, _ = _plan(eng, g, 1 << 12, 1)
