@@ -365,29 +365,10 @@ struct PassOpts {
     const Plan *plan = nullptr;
     bool into = false, finish = true;
 };
-// Shapes of the batched-affine rounds of a pass: per round the launch plan of one pipeline (the whole slot range, or
-// one of its halves when the rounds run as two pipelines), and the scratch one pipeline needs over ALL rounds — the
-// maxima, because the two pipelines may be a round apart and the per-round sizes are not monotone (K shrinks with the
-// slot count, so NT = ⌈slots/K⌉ can grow from one round to the next).
-struct BaLayout {
-    bool split = false;
-    BaPlan bp[3];
-    size_t pre_el = 0, t_el = 0, u_el = 0;   // elements per pipeline: prefix, T / prefix2, U
-};
-BaLayout ba_layout(size_t s1, int R, int sm_count) {
-    static const bool split_ok = !(getenv("B200MSM_BA_SPLIT") && atoi(getenv("B200MSM_BA_SPLIT")) == 0);
-    BaLayout L;
-    L.split = split_ok && s1 >= ((size_t)1 << 20);
-    size_t s_out = s1;
-    for (int r = 0; r < R; r++) {
-        const size_t s_part = L.split ? s_out / 2 + ((size_t)1 << (5 + R)) + 1 : s_out;
-        L.bp[r] = ba_plan(s_part, sm_count);
-        L.pre_el = std::max(L.pre_el, (size_t)L.bp[r].NT * L.bp[r].K);
-        L.t_el = std::max<size_t>(L.t_el, L.bp[r].NT);
-        L.u_el = std::max<size_t>(L.u_el, L.bp[r].NU);
-        s_out = (s_out + 1) / 2;
-    }
-    return L;
+// (environment switch, read once: the rounds as ONE pipeline instead of two interleaved half-range pipelines)
+bool ba_split_ok() {
+    static const bool ok = !(getenv("B200MSM_BA_SPLIT") && atoi(getenv("B200MSM_BA_SPLIT")) == 0);
+    return ok;
 }
 
 // Plan + scratch reservation of one pass (may allocate: never inside a graph capture).
@@ -459,7 +440,7 @@ int pass_prepare(int group, DeviceCtx &cx, const Tun &tn, const void *d_bases_v,
         if (int rc = cx.endo.reserve(n * (size_t)W * 4 * (pl.parts == 4 ? 6 : 1))) return rc;
     if (R > 0) {
         const size_t FB = (size_t)W * 4, s1 = (slots_max + 1) / 2;
-        const BaLayout bl = ba_layout(s1, R, cx.sm_count);
+        const BaLayout bl = ba_layout(s1, R, cx.sm_count, ba_split_ok());
         const size_t np = bl.split ? 2 : 1;
         if (int rc = cx.ba_prefix.reserve((np * bl.pre_el + 256) * FB)) return rc;
         if (int rc = cx.ba_T.reserve((np * bl.t_el + 256) * FB)) return rc;
@@ -534,7 +515,7 @@ int pass_issue_main(DeviceCtx &cx, const PassArgs &pa, cudaStream_t st, bool pro
         // second level + inversion of a round are three small latency-bound launches (≈0.1–0.2 ms in all) during
         // which a single pipeline leaves the GPU almost idle; with two, the other half's large kernels fill it.
         // Each pipeline owns a fixed part of every scratch array for all rounds (ba_layout).
-        const BaLayout bl = ba_layout(s_out, pa.R, cx.sm_count);
+        const BaLayout bl = ba_layout(s_out, pa.R, cx.sm_count, ba_split_ok());
         const bool split = bl.split;
         const int align_log = split ? 6 + pa.R : 0;
         const size_t FW = (size_t)W;   // u32 words per field element

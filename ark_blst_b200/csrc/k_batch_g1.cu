@@ -26,27 +26,6 @@ void launch_accumulate_direct_g1(const uint32_t *pts, const uint32_t *start, con
 }  // namespace b200msm
 
 namespace b200msm {
-// Shape of one round over at most s_out_max output slots: NT threads of K slots each, then NU second-level threads
-// of K2 totals each.  The second level and the inversions are latency-bound (measured at G1 2^20: ≈1.5 µs per
-// dependent product, ≈50 µs per divsteps inversion however few there are), so K is as large as two waves of
-// 3 blocks × 128 threads per SM allow (≤ 32) and K2 keeps the inversions near one warp per scheduler.
-BaPlan ba_plan(size_t s_out_max, int sm_count) {
-    BaPlan bp;
-    const size_t wave = (size_t)sm_count * 3 * 128;
-    size_t K = (s_out_max + 2 * wave - 1) / (2 * wave);
-    K = K < 4 ? 4 : (K > 32 ? 32 : K);
-    size_t NT = (s_out_max + K - 1) / K;
-    NT = (NT + 127) / 128 * 128;
-    if (NT == 0) NT = 128;
-    size_t K2 = (NT + 16383) / 16384;
-    K2 = K2 < 8 ? 8 : (K2 > 64 ? 64 : K2);
-    bp.NT = (uint32_t)NT;
-    bp.K = (uint32_t)K;
-    bp.K2 = (uint32_t)K2;
-    bp.NU = (uint32_t)((NT + K2 - 1) / K2);
-    return bp;
-}
-
 static __global__ void k_dbg_inv_sg(int is_fp2, const uint32_t *in, uint32_t *out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -6,6 +6,8 @@
 #include <cstddef>
 #include <cstdint>
 
+#include "plan.h"
+
 namespace b200msm {
 
 // k_prep.cu
@@ -50,11 +52,9 @@ void launch_heavy_g2(const uint32_t *bases, const uint32_t *vals, const uint32_t
 // k_batch_g{1,2}.cu — batched-affine pairing rounds (batch_affine.cuh).  One round halves the (padded) entry array:
 // first = 1 reads entries through vals from the bases (sign / GLV image applied), else from `src` (the previous
 // round's output).  total_ptr → the scan's grand total (slots of the entry array); round = 0-based; s_out_max bounds
-// the output slots on the host.  Scratch: prefix ≥ NT·K elements, T and prefix2 ≥ NT, U ≥ NU (sizes from ba_plan).
+// the output slots on the host.  Scratch: prefix ≥ NT·K elements, T and prefix2 ≥ NT, U ≥ NU (sizes from plan.h: ba_plan / ba_layout).
 // split_align_log > 0: the launch covers part 0 / 1 of the slot range only (batch_affine.cuh: ba_range); the caller
 // gives each part its own scratch and stream.
-struct BaPlan { uint32_t NT, K, NU, K2; };
-BaPlan ba_plan(size_t s_out_max, int sm_count);
 void launch_ba_round_g1(int first, const uint32_t *src, const uint32_t *vals, const uint32_t *endo_x, uint32_t n_pts,
                         const uint32_t *total_ptr, int round, const BaPlan &bp, uint32_t *prefix, uint32_t *T, uint32_t *prefix2,
                         uint32_t *U, uint32_t *out, cudaStream_t st, int part = 0, int split_align_log = 0, int img_full = 0);

@@ -106,6 +106,56 @@ inline int auto_window(size_t n, bool g2) {  // non-GLV width (scratch estimates
     return pl.c;
 }
 
+// ---- shapes of the batched-affine pairing rounds (batch_affine.cuh) — host arithmetic, unit-tested without a device ----
+// One round over at most s_out_max output slots: NT threads of K slots each, then NU second-level threads of K2 totals
+// each.  The second level and the inversions are latency-bound (measured at G1 2^20: ≈1.5 µs per dependent product,
+// ≈50 µs per divsteps inversion however few there are), so K is as large as two waves of 3 blocks × 128 threads per SM
+// allow (≤ 32) and K2 keeps the inversions near one warp per scheduler.
+struct BaPlan { uint32_t NT, K, NU, K2; };
+inline BaPlan ba_plan(size_t s_out_max, int sm_count) {
+    BaPlan bp;
+    const size_t wave = (size_t)sm_count * 3 * 128;
+    size_t K = (s_out_max + 2 * wave - 1) / (2 * wave);
+    K = K < 4 ? 4 : (K > 32 ? 32 : K);
+    size_t NT = (s_out_max + K - 1) / K;
+    NT = (NT + 127) / 128 * 128;
+    if (NT == 0) NT = 128;
+    size_t K2 = (NT + 16383) / 16384;
+    K2 = K2 < 8 ? 8 : (K2 > 64 ? 64 : K2);
+    bp.NT = (uint32_t)NT;
+    bp.K = (uint32_t)K;
+    bp.K2 = (uint32_t)K2;
+    bp.NU = (uint32_t)((NT + K2 - 1) / K2);
+    return bp;
+}
+// The rounds of a pass: per round the launch plan of one pipeline (the whole slot range, or one of its halves when
+// the rounds run as two pipelines on two streams — from 2^20 output slots), and the scratch ONE pipeline needs over
+// ALL rounds: the maxima, because the two pipelines may be a round apart and the per-round sizes are not monotone
+// (K shrinks with the slot count, so NT = ⌈slots/K⌉ can grow from one round to the next).  A first version placed
+// part 1's scratch by the current round's sizes, a second by the first round's: both lost results (tests/cpp/test_plan.cpp
+// checks that no round of either pipeline ever leaves its part).
+struct BaLayout {
+    bool split = false;
+    BaPlan bp[3];
+    size_t s_part[3] = {0, 0, 0};             // slots one pipeline covers at most, per round
+    size_t pre_el = 0, t_el = 0, u_el = 0;    // elements per pipeline: prefix, T / prefix2, U
+};
+inline BaLayout ba_layout(size_t s1, int R, int sm_count, bool split_ok = true) {
+    BaLayout L;
+    L.split = split_ok && s1 >= ((size_t)1 << 20);
+    size_t s_out = s1;
+    for (int r = 0; r < R && r < 3; r++) {
+        // a half is bounded by half the round's slots plus the boundary's rounding (2^(6+R) entries ≫ r+1 ≤ 2^(5+R))
+        L.s_part[r] = L.split ? s_out / 2 + ((size_t)1 << (5 + R)) + 1 : s_out;
+        L.bp[r] = ba_plan(L.s_part[r], sm_count);
+        L.pre_el = std::max(L.pre_el, (size_t)L.bp[r].NT * L.bp[r].K);
+        L.t_el = std::max<size_t>(L.t_el, L.bp[r].NT);
+        L.u_el = std::max<size_t>(L.u_el, L.bp[r].NU);
+        s_out = (s_out + 1) / 2;
+    }
+    return L;
+}
+
 // Fixed-base window table (table[w][i] = 2^(c·w)·P_i): one bucket set for all windows, no Horner
 // chain, so the width only trades the n·W additions of the accumulation against one window's
 // bucket reduction (+ a log-depth tree) — wider than the plain plan's at every n.

@@ -46,6 +46,30 @@ int main() {
         auto_plan(1u << 20, g2, -1, 0, p); CHECK(p.glv && p.split && p.c == 16 && (p.parts == 2 ? p.nwin == 9 : (g2 && p.parts == 4 && p.nwin == 5)));
         auto_plan(1u << 20, g2, 2, 0, p); CHECK(p.glv && p.split && p.c == 16 && p.nwin == (g2 ? 5 : 9) && p.parts == (g2 ? 4 : 2));
     }
+    // batched-affine rounds: one pipeline's scratch part holds every round of that pipeline, whatever the size —
+    // NT·K covers the slots, and no round needs more than the per-pipeline maxima the layout reserves and offsets by
+    for (int R = 1; R <= 3; R++)
+        for (size_t s1 = 1; s1 < ((size_t)1 << 29); s1 = s1 * 3 / 2 + 977) {
+            for (int split_ok = 0; split_ok <= 1; split_ok++) {
+                BaLayout L = ba_layout(s1, R, 148, split_ok);
+                CHECK(L.split == (split_ok && s1 >= ((size_t)1 << 20)));
+                size_t s_out = s1;
+                for (int r = 0; r < R; r++) {
+                    const BaPlan &b = L.bp[r];
+                    CHECK((size_t)b.NT * b.K >= L.s_part[r] && b.NT % 128 == 0 && b.K >= 4 && b.K <= 32);
+                    CHECK((size_t)b.NU * b.K2 >= b.NT && b.K2 >= 8 && b.K2 <= 64);
+                    CHECK((size_t)b.NT * b.K <= L.pre_el && b.NT <= L.t_el && b.NU <= L.u_el);
+                    // the two halves of a round cover its slots: part 0 ≤ half, part 1 ≤ half + the boundary's rounding
+                    if (L.split) CHECK(2 * L.s_part[r] >= s_out && L.s_part[r] >= s_out / 2 + ((size_t)1 << (5 + R - r - 1)));
+                    else CHECK(L.s_part[r] == s_out);
+                    s_out = (s_out + 1) / 2;
+                }
+            }
+        }
+    {   // the sizes that broke the earlier layouts: NT grows from round 0 to round 1 when K halves with the slot count
+        BaLayout L = ba_layout(5750000, 3, 148, true);
+        CHECK(L.split && L.bp[1].NT > L.bp[0].NT && L.t_el >= L.bp[1].NT);
+    }
     std::printf(failures ? "FAILED (%d)\n" : "ok\n", failures);
     return failures ? 1 : 0;
 }
